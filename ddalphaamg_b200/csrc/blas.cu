@@ -1,0 +1,115 @@
+// blas.cu -- BLAS-1 + reductions (see blas.h)
+#include "blas.h"
+
+namespace dda {
+
+void (*g_allreduce_sum)(double *buf, int n) = nullptr;
+
+static const int MAXV = 64;
+template <class T> struct PtrArr { const cx<T> *p[MAXV]; };
+struct CoefArr { double re[MAXV], im[MAXV]; };
+
+static double *red_buf() {   // device scratch for reduction results
+  static double *b = nullptr;
+  if (!b) b = dev_alloc<double>(4 * (MAXV + 2));
+  return b;
+}
+
+template <class T> void vzero(cx<T> *x, long n) { dev_zero(x, sizeof(cx<T>) * n); }
+template <class T> void vcopy(cx<T> *y, const cx<T> *x, long n) { if (y != x) d2d(y, x, sizeof(cx<T>) * n); }
+template <class T> void vscale(cx<T> *y, const cx<T> *x, double a, long n) {
+  T aa = (T)a;
+  launch_n(n, DLAMBDA(long i) { y[i] = aa * x[i]; });
+}
+template <class T> void vaxpy(cx<T> *y, cd a, const cx<T> *x, long n) {
+  cx<T> aa((T)a.re, (T)a.im);
+  launch_n(n, DLAMBDA(long i) { cx<T> v = y[i]; fma_(v, aa, x[i]); y[i] = v; });
+}
+template <class T> void vxpay(cx<T> *z, const cx<T> *x, cd a, const cx<T> *y, long n) {
+  cx<T> aa((T)a.re, (T)a.im);
+  launch_n(n, DLAMBDA(long i) { cx<T> v = x[i]; fma_(v, aa, y[i]); z[i] = v; });
+}
+template <class T> void vsub(cx<T> *z, const cx<T> *x, const cx<T> *y, long n) { launch_n(n, DLAMBDA(long i) { z[i] = x[i] - y[i]; }); }
+template <class T> void vadd(cx<T> *z, const cx<T> *x, const cx<T> *y, long n) { launch_n(n, DLAMBDA(long i) { z[i] = x[i] + y[i]; }); }
+template <class T, class S> void vcast(cx<T> *y, const cx<S> *x, long n) { launch_n(n, DLAMBDA(long i) { y[i] = cx<T>((T)x[i].re, (T)x[i].im); }); }
+
+template <class T> void vmulti_axpy(cx<T> *y, cx<T> *const *V, const cd *coef, int m, int sign, long n) {
+  DDA_ASSERT(m <= MAXV);
+  if (m <= 0) return;
+  PtrArr<T> pa; CoefArr ca;
+  for (int k = 0; k < m; k++) { pa.p[k] = V[k]; ca.re[k] = sign * coef[k].re; ca.im[k] = sign * coef[k].im; }
+  launch_n(n, DLAMBDA(long i) {
+    cx<T> v = y[i];
+    for (int k = 0; k < m; k++) fma_(v, cx<T>((T)ca.re[k], (T)ca.im[k]), pa.p[k][i]);
+    y[i] = v;
+  });
+}
+
+template <class T> void vmulti_dot(cd *out, cx<T> *const *V, int m, const cx<T> *w, long n) {
+  DDA_ASSERT(m <= MAXV);
+  if (m <= 0) return;
+  PtrArr<T> pa;
+  for (int k = 0; k < m; k++) pa.p[k] = V[k];
+  double *buf = red_buf();
+  launch_reduce<2>(m, n, DLAMBDA(long seg, long i, double *acc) {
+    cx<T> a = pa.p[seg][i], b = w[i];
+    acc[0] += (double)a.re * b.re + (double)a.im * b.im;
+    acc[1] += (double)a.re * b.im - (double)a.im * b.re;
+  }, buf);
+  double h[2 * MAXV];
+  d2h(h, buf, sizeof(double) * 2 * m);
+  if (g_allreduce_sum) g_allreduce_sum(h, 2 * m);
+  for (int k = 0; k < m; k++) out[k] = cd(h[2 * k], h[2 * k + 1]);
+}
+
+template <class T> void vmulti_dot_norm(cd *out, cx<T> *const *V, int m, const cx<T> *w, long n) {
+  DDA_ASSERT(m + 1 <= MAXV);
+  PtrArr<T> pa;
+  for (int k = 0; k < m; k++) pa.p[k] = V[k];
+  pa.p[m] = w;
+  double *buf = red_buf();
+  launch_reduce<2>(m + 1, n, DLAMBDA(long seg, long i, double *acc) {
+    cx<T> a = pa.p[seg][i], b = w[i];
+    acc[0] += (double)a.re * b.re + (double)a.im * b.im;
+    acc[1] += (double)a.re * b.im - (double)a.im * b.re;
+  }, buf);
+  double h[2 * MAXV];
+  d2h(h, buf, sizeof(double) * 2 * (m + 1));
+  if (g_allreduce_sum) g_allreduce_sum(h, 2 * (m + 1));
+  for (int k = 0; k <= m; k++) out[k] = cd(h[2 * k], h[2 * k + 1]);
+}
+
+template <class T> cd vdot(const cx<T> *x, const cx<T> *y, long n) {
+  cd r; cx<T> *v[1] = {const_cast<cx<T> *>(x)};
+  vmulti_dot(&r, v, 1, y, n);
+  return r;
+}
+template <class T> double vnorm2(const cx<T> *x, long n) {
+  double *buf = red_buf();
+  launch_reduce<1>(1, n, DLAMBDA(long seg, long i, double *acc) { (void)seg; cx<T> a = x[i]; acc[0] += (double)a.re * a.re + (double)a.im * a.im; }, buf);
+  double h; d2h(&h, buf, sizeof(double));
+  if (g_allreduce_sum) g_allreduce_sum(&h, 1);
+  return h;
+}
+
+#define INST(T) \
+  template void vzero<T>(cx<T> *, long); \
+  template void vcopy<T>(cx<T> *, const cx<T> *, long); \
+  template void vscale<T>(cx<T> *, const cx<T> *, double, long); \
+  template void vaxpy<T>(cx<T> *, cd, const cx<T> *, long); \
+  template void vxpay<T>(cx<T> *, const cx<T> *, cd, const cx<T> *, long); \
+  template void vsub<T>(cx<T> *, const cx<T> *, const cx<T> *, long); \
+  template void vadd<T>(cx<T> *, const cx<T> *, const cx<T> *, long); \
+  template void vmulti_axpy<T>(cx<T> *, cx<T> *const *, const cd *, int, int, long); \
+  template cd vdot<T>(const cx<T> *, const cx<T> *, long); \
+  template double vnorm2<T>(const cx<T> *, long); \
+  template void vmulti_dot<T>(cd *, cx<T> *const *, int, const cx<T> *, long); \
+  template void vmulti_dot_norm<T>(cd *, cx<T> *const *, int, const cx<T> *, long);
+INST(float)
+INST(double)
+template void vcast<float, double>(cf *, const cd *, long);
+template void vcast<double, float>(cd *, const cf *, long);
+template void vcast<float, float>(cf *, const cf *, long);
+template void vcast<double, double>(cd *, const cd *, long);
+
+}  // namespace dda

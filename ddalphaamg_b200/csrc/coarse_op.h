@@ -1,0 +1,38 @@
+// coarse_op.h -- coarse-grid operator (levels >= 1): storage and kernels.
+//
+//   (D_c phi)(x) = S(x) phi(x) + sum_mu [ F_mu(x) phi(x+mu) + G5 F_mu(x-mu)^H G5 phi(x-mu) ],   G5 = diag(1_Nv, -1_Nv)
+// S(x) and the four forward hops F_mu(x) are dense n x n complex matrices (n = 2 Nv), column-major; the backward hop
+// is the gamma5-conjugate transpose of the neighbour's forward hop, exactly the block structure
+// [A^H -C^H; -B^H D^H] the reference uses (coarse_operator_generic.h:119-172).  Reference counterparts:
+// apply_coarse_operator_PRECISION (coarse_operator_generic.c:383-395), coarse_self_couplings (:288-315),
+// coarse_hopping_term / coarse_n_hopping_term (coarse_oddeven_generic.c:447-728), coarse_block_operator
+// (coarse_operator_generic.c:208-236), coarse_diag_ee / coarse_diag_oo_inv (coarse_oddeven_generic.c:123-198).
+// The hop matrices here carry the operator's sign (F = P^H H P with H = -(1-gamma_mu) D_mu on the fine level).
+#pragma once
+#include "common.cuh"
+#include "lattice.h"
+#include "fine_op.h"
+
+namespace dda {
+
+struct CoarseOp {
+  int n = 0;                 // complex dofs per site
+  long V = 0;
+  cf *F = nullptr;           // [site][mu][n*n] column-major forward hops
+  cf *S = nullptr;           // [site][n*n] column-major self coupling
+  cf *Sinv = nullptr;        // coarsest level: inverse self coupling of the odd sites, [site - n_even][n*n] column-major
+  long n_even = 0;
+  const int *nb = nullptr;
+  const unsigned char *blkflag = nullptr, *aggflag = nullptr;
+};
+
+// generic masked apply, same selectors as fine_apply.  self: SELF_C -> S, SELF_CINV -> Sinv (odd sites only).
+void coarse_apply(const CoarseOp &op, cf *out, const cf *in, SiteSel sel, int hop, int dir, int self, int outmode,
+                  const cf *eta = nullptr, const cf *in_self = nullptr);
+// Sinv = S^{-1} on the odd sites of the coarsest level (dense inversion in double, no pivoting; the reference
+// factorises LU without pivoting, coarse_oddeven_generic.c:24-73)
+void coarse_invert_odd_self(CoarseOp &op);
+// optimised full-lattice apply (sm_100a only; coarse_kernel.cu)
+void coarse_apply_fast(const CoarseOp &op, cf *out, const cf *in);
+
+}  // namespace dda

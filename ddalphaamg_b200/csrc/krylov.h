@@ -1,0 +1,105 @@
+// krylov.h -- restarted, right-preconditioned flexible GMRES driven from the host, vectors on the device.
+// Behaviour follows the reference's fgmres_PRECISION (linsolve_generic.c:219-413), arnoldi_step (default variant,
+// :809-895), qr_update (:898-940) and compute_solution (:943-982).  One fused multi-dot launch + one norm launch
+// per Arnoldi step; Hessenberg / Givens scalars live on the host in double.
+#pragma once
+#include "common.cuh"
+#include "blas.h"
+
+namespace dda {
+
+template <class T> struct Fgmres {
+  typedef cx<T> C;
+  long n = 0;
+  int m = 0, max_restart = 0;
+  double tol = 0;
+  bool flexible = false, allocated = false;
+  std::vector<C *> V, Z;
+  C *w = nullptr, *r = nullptr;
+  std::vector<cd> H, gamma, c, s, y;   // H column-major: H[j*(m+1)+i]
+  std::function<void(C *, const C *)> op, prec;
+  int last_iter = 0;
+  double last_relres = 0;
+
+  void alloc(long n_, int m_, int max_restart_, double tol_, bool flexible_) {
+    release();
+    n = n_; m = m_; max_restart = max_restart_; tol = tol_; flexible = flexible_;
+    V.resize(m + 1); for (auto &v : V) v = dev_alloc<C>(n);
+    if (flexible) { Z.resize(m); for (auto &z : Z) z = dev_alloc<C>(n); }
+    w = dev_alloc<C>(n); r = dev_alloc<C>(n);
+    H.assign((size_t)(m + 1) * m, cd(0, 0)); gamma.assign(m + 1, cd(0, 0)); c.assign(m, cd(0, 0)); s.assign(m, cd(0, 0)); y.assign(m, cd(0, 0));
+    allocated = true;
+  }
+  void release() {
+    for (auto v : V) dev_free(v);
+    for (auto z : Z) dev_free(z);
+    V.clear(); Z.clear();
+    dev_free(w); dev_free(r); w = r = nullptr; allocated = false;
+  }
+  cd &h(int i, int j) { return H[(size_t)j * (m + 1) + i]; }
+
+  // solves op x = b.  zero_guess: x is taken as 0 on entry.  Returns the number of iterations.
+  int solve(C *x, const C *b, bool zero_guess) {
+    DDA_ASSERT(allocated && op);
+    int iter = 0, finish = 0, j = -1;
+    double norm_r0 = 1, gamma_jp1 = 1;
+    for (int ol = 0; ol < max_restart && !finish; ol++) {
+      bool nores = (ol == 0 && zero_guess);
+      if (nores) vcopy(r, b, n);
+      else { op(w, x); vsub(r, b, w, n); }
+      double g0 = std::sqrt(vnorm2(r, n));
+      gamma[0] = cd(g0, 0);
+      if (ol == 0) norm_r0 = g0;
+      if (g0 == 0.0) { if (nores) vzero(x, n); last_relres = 0; break; }
+      vscale(V[0], r, 1.0 / g0, n);
+      j = -1;
+      for (int il = 0; il < m && !finish; il++) {
+        j = il; iter++;
+        const C *zj = V[j];
+        if (prec) { prec(Z[j], V[j]); zj = Z[j]; }
+        op(w, zj);
+        std::vector<cd> hcol(j + 2);
+        vmulti_dot(hcol.data(), V.data(), j + 1, w, n);
+        for (int i = 0; i <= j; i++) h(i, j) = hcol[i];
+        vmulti_axpy(w, V.data(), hcol.data(), j + 1, -1, n);
+        double hn = std::sqrt(vnorm2(w, n));
+        h(j + 1, j) = cd(hn, 0);
+        if (hn > 1e-15) vscale(V[j + 1], w, 1.0 / hn, n);
+        if (hn > tol / 10) {
+          // Givens update
+          for (int i = 0; i < j; i++) {
+            cd beta = (-s[i]) * h(i, j) + c[i] * h(i + 1, j);
+            h(i, j) = conj(c[i]) * h(i, j) + conj(s[i]) * h(i + 1, j);
+            h(i + 1, j) = beta;
+          }
+          double bn = std::sqrt(norm2(h(j, j)) + norm2(h(j + 1, j)));
+          s[j] = cd(h(j + 1, j).re / bn, h(j + 1, j).im / bn); c[j] = cd(h(j, j).re / bn, h(j, j).im / bn);
+          gamma[j + 1] = (-s[j]) * gamma[j]; gamma[j] = conj(c[j]) * gamma[j];
+          h(j, j) = cd(bn, 0); h(j + 1, j) = cd(0, 0);
+          gamma_jp1 = std::sqrt(norm2(gamma[j + 1]));
+          if (gamma_jp1 / norm_r0 < tol || gamma_jp1 / norm_r0 > 1e5) {
+            finish = 1;
+            if (gamma_jp1 / norm_r0 > 1e5) fprintf(stderr, "dd_alpha_amg_b200: divergence of fgmres, iter = %d\n", iter);
+          }
+        } else { finish = 1; break; }
+      }
+      // back substitution + solution update (x = or += sum y_i Z_i)
+      if (j >= 0) {
+        for (int i = j; i >= 0; i--) {
+          cd yi = gamma[i];
+          for (int k = i + 1; k <= j; k++) yi -= h(i, k) * y[k];
+          double d = norm2(h(i, i)); cd hi = h(i, i);
+          y[i] = cd((yi.re * hi.re + yi.im * hi.im) / d, (yi.im * hi.re - yi.re * hi.im) / d);
+        }
+        std::vector<C *> &B = prec ? Z : V;
+        if (nores) vzero(x, n);
+        vmulti_axpy(x, B.data(), y.data(), j + 1, +1, n);
+      }
+      last_relres = gamma_jp1 / norm_r0;
+    }
+    last_iter = iter;
+    return iter;
+  }
+};
+
+}  // namespace dda

@@ -1,0 +1,105 @@
+// lattice.cu -- builds the site ordering and neighbour / boundary-flag tables of one level (host, once).
+#include "lattice.h"
+
+namespace dda {
+
+void Geometry::build() {
+  V = (long)L[0] * L[1] * L[2] * L[3];
+  DDA_ASSERT(V > 0 && V < (1L << 31));
+  const bool last = coarsest();
+  int Bq[4], Aq[4];
+  for (int m = 0; m < 4; m++) {
+    Aq[m] = last ? L[m] : A[m];
+    Bq[m] = last ? L[m] : B[m];
+    DDA_ASSERT(L[m] % Aq[m] == 0 && Aq[m] % Bq[m] == 0);
+  }
+  bs = Bq[0] * Bq[1] * Bq[2] * Bq[3];
+  as = Aq[0] * Aq[1] * Aq[2] * Aq[3];
+  nblocks = (int)(V / bs);
+  nagg = (int)(V / as);
+  if (sh > 0) DDA_ASSERT(V % (1L << sh) == 0);
+
+  // in-block position table
+  std::vector<int> inblock(bs);
+  {
+    int ne = 0, no = 0, k = 0;
+    for (int t = 0; t < Bq[0]; t++) for (int z = 0; z < Bq[1]; z++) for (int y = 0; y < Bq[2]; y++) for (int x = 0; x < Bq[3]; x++, k++)
+      if (((t + z + y + x) & 1) == 0) ne++;
+    bs_even = ne;
+    int ce = 0; no = 0; k = 0;
+    for (int t = 0; t < Bq[0]; t++) for (int z = 0; z < Bq[1]; z++) for (int y = 0; y < Bq[2]; y++) for (int x = 0; x < Bq[3]; x++, k++) {
+      if (block_eo && !last) { if (((t + z + y + x) & 1) == 0) inblock[k] = ce++; else inblock[k] = ne + no++; }
+      else inblock[k] = k;
+    }
+  }
+  lex2nat.assign(V, 0); nat2lex.assign(V, 0);
+  block_color.assign(nblocks, 0);
+  std::vector<int> coord(4 * V);
+  if (last && global_eo) {
+    long ne = 0;
+    for (int t = 0; t < L[0]; t++) for (int z = 0; z < L[1]; z++) for (int y = 0; y < L[2]; y++) for (int x = 0; x < L[3]; x++)
+      if (((t + z + y + x) & 1) == 0) ne++;
+    n_even = ne;
+    long ce = 0, co = 0;
+    for (int t = 0; t < L[0]; t++) for (int z = 0; z < L[1]; z++) for (int y = 0; y < L[2]; y++) for (int x = 0; x < L[3]; x++) {
+      long i = lex(t, z, y, x);
+      long k = (((t + z + y + x) & 1) == 0) ? ce++ : ne + co++;
+      lex2nat[i] = (int)k;
+    }
+  } else {
+    int na[4], nbpa[4];
+    for (int m = 0; m < 4; m++) { na[m] = L[m] / Aq[m]; nbpa[m] = Aq[m] / Bq[m]; }
+    int bpa = nbpa[0] * nbpa[1] * nbpa[2] * nbpa[3];
+    for (int t = 0; t < L[0]; t++) for (int z = 0; z < L[1]; z++) for (int y = 0; y < L[2]; y++) for (int x = 0; x < L[3]; x++) {
+      int c[4] = {t, z, y, x};
+      long ai = 0, bi = 0, li = 0; int bsum = 0;
+      for (int m = 0; m < 4; m++) {
+        ai = ai * na[m] + c[m] / Aq[m];
+        bi = bi * nbpa[m] + (c[m] % Aq[m]) / Bq[m];
+        li = li * Bq[m] + c[m] % Bq[m];
+        bsum += c[m] / Bq[m];
+      }
+      long blk = ai * bpa + bi;
+      lex2nat[lex(t, z, y, x)] = (int)(blk * bs + inblock[li]);
+      block_color[blk] = bsum & 1;
+    }
+    n_even = bs_even;
+  }
+  for (int t = 0; t < L[0]; t++) for (int z = 0; z < L[1]; z++) for (int y = 0; y < L[2]; y++) for (int x = 0; x < L[3]; x++) {
+    long i = lex(t, z, y, x); int k = lex2nat[i];
+    nat2lex[k] = (int)i;
+    coord[4 * (long)k + 0] = t; coord[4 * (long)k + 1] = z; coord[4 * (long)k + 2] = y; coord[4 * (long)k + 3] = x;
+  }
+  h_nb.assign(8 * V, 0);
+  std::vector<unsigned char> bf(V, 0), af(V, 0);
+  for (long k = 0; k < V; k++) {
+    int *c = &coord[4 * k];
+    for (int m = 0; m < 4; m++) {
+      int cp[4] = {c[0], c[1], c[2], c[3]}, cm[4] = {c[0], c[1], c[2], c[3]};
+      cp[m] = (c[m] + 1) % L[m]; cm[m] = (c[m] + L[m] - 1) % L[m];
+      h_nb[(long)m * V + k] = lex2nat[lex(cp[0], cp[1], cp[2], cp[3])];
+      h_nb[(long)(4 + m) * V + k] = lex2nat[lex(cm[0], cm[1], cm[2], cm[3])];
+      if (c[m] % Bq[m] == Bq[m] - 1) bf[k] |= (unsigned char)(1u << m);
+      if (c[m] % Bq[m] == 0) bf[k] |= (unsigned char)(1u << (4 + m));
+      if (c[m] % Aq[m] == Aq[m] - 1) af[k] |= (unsigned char)(1u << m);
+      if (c[m] % Aq[m] == 0) af[k] |= (unsigned char)(1u << (4 + m));
+    }
+  }
+  d_nb = dev_upload(h_nb);
+  d_blkflag = dev_upload(bf);
+  d_aggflag = dev_upload(af);
+  d_lex2nat = dev_upload(lex2nat);
+  d_nat2lex = dev_upload(nat2lex);
+  std::vector<int> lists[2];
+  for (int b = 0; b < nblocks; b++) lists[block_color[b]].push_back(b);
+  for (int c = 0; c < 2; c++) { nblk_color[c] = (int)lists[c].size(); d_blocklist[c] = dev_upload(lists[c]); }
+}
+
+void Geometry::destroy() {
+  dev_free(d_nb); dev_free(d_blkflag); dev_free(d_aggflag); dev_free(d_lex2nat); dev_free(d_nat2lex);
+  dev_free(d_blocklist[0]); dev_free(d_blocklist[1]); dev_free(d_agg2coarse);
+  d_nb = nullptr; d_blkflag = d_aggflag = nullptr; d_lex2nat = d_nat2lex = nullptr;
+  d_blocklist[0] = d_blocklist[1] = nullptr; d_agg2coarse = nullptr;
+}
+
+}  // namespace dda

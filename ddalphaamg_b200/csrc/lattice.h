@@ -1,0 +1,50 @@
+// lattice.h -- per-level lattice geometry, site ordering and index tables.
+//
+// Native site order of a level (all device vectors of the level use it):
+//   aggregates (lexicographic, T slowest) -> Schwarz blocks inside the aggregate (lexicographic)
+//   -> sites of the block: fine level = even sites then odd sites (parity relative to the block origin),
+//      coarse intermediate levels = lexicographic;
+//   coarsest level: all even sites (lexicographic) then all odd sites (global even-odd order).
+// This is the same ordering idea the reference uses for its Schwarz-ordered operator
+// (schwarz_generic.c:368-474) and its coarsest even-odd operator (data_layout.c:43-100), but here it is the
+// ONLY order of the level: the outer double-precision solver runs in it too, so no per-iteration
+// lexicographic<->Schwarz permutation (reference trans_PRECISION, schwarz_generic.c:1807-1846) is needed.
+#pragma once
+#include "common.cuh"
+
+namespace dda {
+
+enum { T_ = 0, Z_ = 1, Y_ = 2, X_ = 3 };
+
+struct Geometry {
+  int L[4] = {0, 0, 0, 0};   // local lattice, order T Z Y X
+  int B[4] = {0, 0, 0, 0};   // Schwarz block
+  int A[4] = {0, 0, 0, 0};   // aggregate (= coarsening towards the next level); A[0]==0 on the coarsest level
+  long V = 0;                // sites
+  int nc = 12;               // complex dofs per site
+  int sh = 0;                // tile shift of the vector layout (5 on the fine level)
+  bool block_eo = false;     // even-odd order inside blocks
+  bool global_eo = false;    // coarsest level: global even-odd order
+  int bs = 0, nblocks = 0, nblk_color[2] = {0, 0};
+  int as = 0, nagg = 0;
+  long n_even = 0;           // global_eo: number of even sites; block_eo: even sites per block (bs_even)
+  int bs_even = 0;
+  std::vector<int> lex2nat, nat2lex, block_color;
+  std::vector<int> h_nb;     // [8][V]
+  // device tables
+  int *d_nb = nullptr;                 // [8][V] dir 0..3 = +T,+Z,+Y,+X ; 4..7 = -T,-Z,-Y,-X
+  unsigned char *d_blkflag = nullptr;  // bit d: neighbour d is outside the Schwarz block
+  unsigned char *d_aggflag = nullptr;  // bit d: neighbour d is outside the aggregate
+  int *d_blocklist[2] = {nullptr, nullptr};
+  int *d_lex2nat = nullptr, *d_nat2lex = nullptr;
+  int *d_agg2coarse = nullptr;         // aggregate index -> native site index on the next coarser level
+
+  Lay lay() const { Lay l; l.nc = nc; l.sh = sh; return l; }
+  long vlen() const { return V * nc; }   // complex elements of a vector
+  bool coarsest() const { return A[0] == 0; }
+  void build();
+  void destroy();
+  long lex(int t, int z, int y, int x) const { return x + (long)L[3] * (y + (long)L[2] * (z + (long)L[1] * t)); }
+};
+
+}  // namespace dda

@@ -1,0 +1,135 @@
+// solver_fine.cu -- fine-level operator storage: gauge upload, clover construction, float copy, mass shift.
+// Reference counterparts: dd_alpha_amg_set_conf (dd_alpha_amg.c:188-250), dirac_setup (dirac.c:60-170),
+// schwarz_PRECISION_setup (schwarz_generic.c:1037-1074, double -> float Schwarz-ordered copy),
+// schwarz_PRECISION_oddeven_setup (oddeven_generic.c:918-971), shift_update (dirac.c:669-691).
+#include "solver.h"
+
+namespace dda {
+
+Solver *g_solver = nullptr;
+
+void solver_alloc_fine(Solver &s) {
+  DDA_ASSERT(!s.fine_alloc);
+  Level &L = s.lev[0];
+  const Params &p = s.p;
+  L.depth = 0;
+  Geometry &g = L.geo;
+  for (int m = 0; m < 4; m++) {
+    g.L[m] = p.local_lattice[0][m];
+    if (p.num_levels > 1) {
+      g.B[m] = p.block_lattice[0][m];
+      g.A[m] = p.global_lattice[0][m] / p.global_lattice[1][m];
+    } else { g.B[m] = 0; g.A[m] = 0; }
+  }
+  g.nc = 12;
+  long V = (long)g.L[0] * g.L[1] * g.L[2] * g.L[3];
+  g.sh = (V % 32 == 0) ? 5 : 0;
+  g.block_eo = (p.num_levels > 1);
+  g.global_eo = false;
+  g.build();
+  L.Dd = dev_alloc<cd>(V * 36); L.Cd = dev_alloc<double>(V * 72);
+  L.Df = dev_alloc<cf>(V * 36); L.Cf = dev_alloc<float>(V * 72); L.Cinvf = dev_alloc<float>(V * 72);
+  s.lexbuf = dev_alloc<cd>(V * 36);
+  s.xb = dev_alloc<cd>(V * 12); s.xx = dev_alloc<cd>(V * 12);
+  L.opd.D = L.Dd; L.opd.C = L.Cd; L.opd.Cinv = nullptr; L.opd.nb = g.d_nb; L.opd.blkflag = g.d_blkflag; L.opd.aggflag = g.d_aggflag; L.opd.V = V; L.opd.sh = g.sh;
+  L.opf.D = L.Df; L.opf.C = L.Cf; L.opf.Cinv = L.Cinvf; L.opf.nb = g.d_nb; L.opf.blkflag = g.d_blkflag; L.opf.aggflag = g.d_aggflag; L.opf.V = V; L.opf.sh = g.sh;
+  s.fine_alloc = true;
+}
+
+void solver_free_fine(Solver &s) {
+  if (!s.fine_alloc) return;
+  Level &L = s.lev[0];
+  dev_free(L.Dd); dev_free(L.Cd); dev_free(L.Df); dev_free(L.Cf); dev_free(L.Cinvf);
+  dev_free(s.lexbuf); dev_free(s.xb); dev_free(s.xx);
+  L.Dd = nullptr; L.Cd = nullptr; L.Df = nullptr; L.Cf = L.Cinvf = nullptr; s.lexbuf = s.xb = s.xx = nullptr;
+  L.geo.destroy();
+  s.fine_alloc = false;
+}
+
+void solver_upload_conf(Solver &s, const double *gauge_lex) {
+  Level &L = s.lev[0];
+  long V = L.geo.V;
+  h2d(s.lexbuf, gauge_lex, sizeof(cd) * 36 * V);
+  spinor_from_lex<double>(L.geo, L.Dd, s.lexbuf, 36);
+  vscale(L.Dd, L.Dd, 0.5, V * 36);                       // reference stores D = U/2 (dirac.c:80)
+  fine_build_clover(L.geo, L.Dd, L.Cd, s.p.m0, s.p.csw, &s.plaq);
+  s.m0_op = s.p.m0;
+  solver_refresh_float_op(s);
+  s.conf_set = true;
+}
+
+void solver_refresh_float_op(Solver &s) {
+  Level &L = s.lev[0];
+  long V = L.geo.V;
+  cast_links(L.Dd, L.Df, V * 36);
+  cast_reals(L.Cd, L.Cf, V * 72);
+  double *tmp = dev_alloc<double>(V * 72);
+  fine_invert_clover(L.geo, L.Cd, tmp);
+  cast_reals(tmp, L.Cinvf, V * 72);
+  dev_sync();
+  dev_free(tmp);
+}
+
+// host mirrors in the reference's array formats: D[36*site + 9*mu + 3*r + c] complex, clover[42*site + k] complex
+void solver_sync_host_mirrors(Solver &s, bool to_device) {
+  Level &L = s.lev[0];
+  long V = L.geo.V;
+  s.h_gauge.resize((size_t)V * 72); s.h_clover.resize((size_t)V * 84);
+  std::vector<double> c72((size_t)V * 72);
+  if (!to_device) {
+    spinor_to_lex<double>(L.geo, s.lexbuf, L.Dd, 36);
+    d2h(s.h_gauge.data(), s.lexbuf, sizeof(cd) * 36 * V);
+    reals_to_lex(L.geo, (double *)s.lexbuf, L.Cd, 72);
+    d2h(c72.data(), s.lexbuf, sizeof(double) * 72 * V);
+    for (long i = 0; i < V; i++) {
+      for (int k = 0; k < 12; k++) { s.h_clover[84 * i + 2 * k] = c72[72 * i + k]; s.h_clover[84 * i + 2 * k + 1] = 0.0; }
+      for (int k = 0; k < 60; k++) s.h_clover[84 * i + 24 + k] = c72[72 * i + 12 + k];
+    }
+  } else {
+    h2d(s.lexbuf, s.h_gauge.data(), sizeof(cd) * 36 * V);
+    spinor_from_lex<double>(L.geo, L.Dd, s.lexbuf, 36);
+    for (long i = 0; i < V; i++) {
+      for (int k = 0; k < 12; k++) c72[72 * i + k] = s.h_clover[84 * i + 2 * k];
+      for (int k = 0; k < 60; k++) c72[72 * i + 12 + k] = s.h_clover[84 * i + 24 + k];
+    }
+    h2d(s.lexbuf, c72.data(), sizeof(double) * 72 * V);
+    reals_from_lex(L.geo, L.Cd, (const double *)s.lexbuf, 72);
+    solver_refresh_float_op(s);
+  }
+}
+
+void solver_shift_mass(Solver &s, double new_m0) {
+  double delta = new_m0 - s.m0_op;
+  if (delta == 0.0) return;
+  Level &L = s.lev[0];
+  fine_shift_clover(L.geo, L.Cd, delta);
+  solver_refresh_float_op(s);
+  if (s.setup_done) {
+    for (int d = 1; d < s.nlev; d++) {
+      CoarseOp &c = s.lev[d].cop;
+      cf *S = c.S; int n = c.n; float df = (float)delta;
+      launch_n(c.V * n, DLAMBDA(long i) { long site = i / n; int r = (int)(i - site * n); S[site * (long)n * n + (long)r * n + r].re += df; });
+      if (s.lev[d].last) coarse_invert_odd_self(c);
+    }
+  }
+  s.m0_op = new_m0;
+}
+
+template <class T> void dw_apply_fast(const FineOp<T> &op, cx<T> *out, const cx<T> *in);
+
+template <> void solver_apply_dw<double>(Solver &s, cd *out, const cd *in) {
+  Level &L = s.lev[0];
+#ifndef DDA_HOST_EMU
+  if (s.use_fast && L.geo.sh == 5) { dw_apply_fast<double>(L.opd, out, in); return; }
+#endif
+  fine_apply<double>(L.opd, out, in, sel_all(L.geo.V), HOP_ALL, 0, SELF_C, OUT_SET);
+}
+template <> void solver_apply_dw<float>(Solver &s, cf *out, const cf *in) {
+  Level &L = s.lev[0];
+#ifndef DDA_HOST_EMU
+  if (s.use_fast && L.geo.sh == 5) { dw_apply_fast<float>(L.opf, out, in); return; }
+#endif
+  fine_apply<float>(L.opf, out, in, sel_all(L.geo.V), HOP_ALL, 0, SELF_C, OUT_SET);
+}
+
+}  // namespace dda

@@ -1,0 +1,372 @@
+"""ctypes host side of libdd_alpha_amg.so -- mirrors the reference's C library interface.
+
+Reference: include/dd_alpha_amg.h:29-83 (dd_alpha_amg_par, dd_alpha_amg_init/set_conf/setup/setup_update/
+wilson_solve/free), include/dd_alpha_amg_parameters.h:25-51, parameter file keys src/init.c:592-962.
+"""
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STRINGLENGTH = 500
+MAX_MG_LEVELS = 4
+
+
+class INFO:
+    NUM_LEVELS, SITES, SITE_VARS, TEST_VECTORS, BLOCK_SITES, NUM_BLOCKS, EMULATION = range(7)
+
+
+class OPT:
+    USE_FAST, PROFILE, SEED, PRINT = range(4)
+
+
+class STAT:
+    LAUNCHES, DEVICE_BYTES, PLAQUETTE, ITER, COARSE_ITER, T_COARSEST, T_RESTRICT, T_INTERPOLATE = range(8)
+    T_SMOOTH0 = 10
+    T_OP0 = 20
+
+
+class OP:
+    APPLY, RESTRICT, INTERPOLATE, SMOOTHER, VCYCLE, COARSEST_SOLVE = range(6)
+
+
+class BENCH:
+    DW_DOUBLE, DW_FLOAT, LEVEL_APPLY, RESTRICT, INTERPOLATE, SMOOTHER, VCYCLE = range(7)
+
+
+CONF_INDEX_FCT = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
+VECTOR_INDEX_FCT = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
+GLOBAL_TIME_FCT = C.CFUNCTYPE(C.c_int, C.c_int)
+
+
+class AmgParameters(C.Structure):
+    """struct dd_alpha_amg_parameters (reference include/dd_alpha_amg_parameters.h:26-51)."""
+    _fields_ = [("number_of_levels", C.c_int),
+                ("global_lattice", (C.c_int * 4) * MAX_MG_LEVELS),
+                ("local_lattice", (C.c_int * 4) * MAX_MG_LEVELS),
+                ("block_lattice", (C.c_int * 4) * MAX_MG_LEVELS),
+                ("mg_basis_vectors", C.c_int * MAX_MG_LEVELS),
+                ("setup_iterations", C.c_int * MAX_MG_LEVELS),
+                ("discard_setup_after", C.c_int),
+                ("update_setup_iterations", C.c_int * MAX_MG_LEVELS),
+                ("update_setup_after", C.c_int),
+                ("post_smooth_iterations", C.c_int * MAX_MG_LEVELS),
+                ("post_smooth_block_iterations", C.c_int * MAX_MG_LEVELS),
+                ("coarse_grid_iterations", C.c_int),
+                ("coarse_grid_maximum_number_of_restarts", C.c_int),
+                ("coarse_grid_tolerance", C.c_double),
+                ("solver_mass", C.c_double),
+                ("setup_mass", C.c_double),
+                ("c_sw", C.c_double)]
+
+
+class Par(C.Structure):
+    """dd_alpha_amg_par (reference include/dd_alpha_amg.h:29-39), passed by value."""
+    _fields_ = [("param_file_path", C.c_char * STRINGLENGTH),
+                ("conf_index_fct", CONF_INDEX_FCT),
+                ("vector_index_fct", VECTOR_INDEX_FCT),
+                ("global_time", GLOBAL_TIME_FCT),
+                ("bc", C.c_int),
+                ("m0", C.c_double),
+                ("csw", C.c_double),
+                ("setup_m0", C.c_double),
+                ("amg_params", AmgParameters)]
+
+
+EXPORTS = ["dd_alpha_amg_init", "dd_alpha_amg_init_external_threading", "dd_alpha_amg_get_gauge_pointer",
+           "dd_alpha_amg_get_clover_pointer", "dd_alpha_amg_fields_updated", "dd_alpha_amg_set_conf",
+           "dd_alpha_amg_update_parameters", "dd_alpha_amg_setup", "dd_alpha_amg_setup_external_threading",
+           "dd_alpha_amg_setup_update", "dd_alpha_amg_setup_update_external_threading", "dd_alpha_amg_wilson_solve",
+           "dd_alpha_amg_preconditioner", "dd_alpha_amg_preconditioner_external_threading", "dd_alpha_amg_free",
+           "DDalphaAMG_initialize", "DDalphaAMG_update_parameters", "DDalphaAMG_setup", "DDalphaAMG_solve",
+           "DDalphaAMG_finalize",
+           "dda_info", "dda_set_option", "dda_get_stat", "dda_reset_stats", "dda_apply_dw", "dda_get_operator",
+           "dda_set_interpolation", "dda_get_interpolation", "dda_level_op", "dda_bench_op", "dda_upload_source",
+           "dda_solve_device", "dda_download_solution"]
+
+
+def library_path():
+    return os.path.join(_HERE, "libdd_alpha_amg.so")
+
+
+_LIBS = {}
+
+
+def load_library(path=None):
+    """Loads the C-ABI library.  Default = the CUDA build; raises if it is missing (no fallback of any kind)."""
+    path = path or library_path()
+    if path in _LIBS:
+        return _LIBS[path]
+    if not os.path.exists(path):
+        raise RuntimeError("%s not found: build the CUDA library with `python -m ddalphaamg_b200.build` "
+                           "(there is no CPU fallback)" % path)
+    L = C.CDLL(path, mode=C.RTLD_LOCAL)
+    dp, fp, ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int)
+    L.dd_alpha_amg_init.argtypes = [Par]
+    L.dd_alpha_amg_init_external_threading.argtypes = [Par, C.c_int, C.c_int]
+    L.dd_alpha_amg_set_conf.argtypes = [dp]
+    L.dd_alpha_amg_set_conf.restype = C.c_double
+    L.dd_alpha_amg_get_gauge_pointer.restype = dp
+    L.dd_alpha_amg_get_clover_pointer.restype = dp
+    L.dd_alpha_amg_update_parameters.argtypes = [C.POINTER(AmgParameters)]
+    L.dd_alpha_amg_setup.argtypes = [C.c_int, ip]
+    L.dd_alpha_amg_setup_update.argtypes = [C.c_int, ip]
+    L.dd_alpha_amg_wilson_solve.argtypes = [dp, dp, C.c_double, C.c_double, C.c_double, ip]
+    L.dd_alpha_amg_wilson_solve.restype = C.c_double
+    L.dd_alpha_amg_preconditioner.argtypes = [dp, dp, C.c_double, C.c_double, ip]
+    L.DDalphaAMG_solve.argtypes = [dp, dp, C.c_double, ip]
+    L.DDalphaAMG_solve.restype = C.c_double
+    L.dda_info.argtypes = [C.c_int, C.c_int]
+    L.dda_info.restype = C.c_int
+    L.dda_set_option.argtypes = [C.c_int, C.c_double]
+    L.dda_get_stat.argtypes = [C.c_int]
+    L.dda_get_stat.restype = C.c_double
+    L.dda_apply_dw.argtypes = [C.c_int, dp, dp]
+    L.dda_get_operator.argtypes = [dp, dp]
+    L.dda_set_interpolation.argtypes = [C.c_int, fp]
+    L.dda_get_interpolation.argtypes = [C.c_int, fp]
+    L.dda_level_op.argtypes = [C.c_int, C.c_int, fp, fp, C.c_int, C.c_int]
+    L.dda_bench_op.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.dda_bench_op.restype = C.c_double
+    L.dda_upload_source.argtypes = [dp]
+    L.dda_solve_device.argtypes = [C.c_double, ip, dp]
+    L.dda_solve_device.restype = C.c_double
+    L.dda_download_solution.argtypes = [dp]
+    _LIBS[path] = L
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def write_ini(path, lattice, block, levels=2, test_vectors=(20, 28), setup_iter=(4, 3), post_smooth=(2, 2),
+              block_iter=(4, 4), m0=-0.5, csw=1.0, tol=1e-10, restart=50, max_restart=20, coarse_tol=5e-2,
+              coarse_iter=100, coarse_restart=5, mixed_precision=1, anti_pbc=1, method=2, kcycle=1,
+              coarse_lattice=None, coarse_block=None, odd_even=1, local_lattice=None):
+    """Parameter file in the reference's "key: value" format (keys: src/init.c:592-962, sample.ini)."""
+    loc = local_lattice or lattice
+    lines = ["configuration: none", "format: 0", "right hand side: 0",
+             "antiperiodic boundary conditions: %d" % anti_pbc, "number of levels: %d" % levels,
+             "number of openmp threads: 1",
+             "d0 global lattice: %d %d %d %d" % tuple(lattice), "d0 local lattice: %d %d %d %d" % tuple(loc),
+             "d0 block lattice: %d %d %d %d" % tuple(block)]
+    for d in range(max(levels - 1, 1)):
+        lines += ["d%d post smooth iter: %d" % (d, post_smooth[min(d, len(post_smooth) - 1)]),
+                  "d%d block iter: %d" % (d, block_iter[min(d, len(block_iter) - 1)]),
+                  "d%d test vectors: %d" % (d, test_vectors[min(d, len(test_vectors) - 1)]),
+                  "d%d setup iter: %d" % (d, setup_iter[min(d, len(setup_iter) - 1)])]
+    if levels > 2:
+        cl = coarse_lattice or [a // b for a, b in zip(lattice, block)]
+        lines += ["d1 global lattice: %d %d %d %d" % tuple(cl), "d1 local lattice: %d %d %d %d" % tuple(cl)]
+        if coarse_block is not None:
+            lines += ["d1 block lattice: %d %d %d %d" % tuple(coarse_block)]
+    lines += ["m0: %.16g" % m0, "csw: %.16g" % csw, "tolerance for relative residual: %g" % tol,
+              "iterations between restarts: %d" % restart, "maximum of restarts: %d" % max_restart,
+              "coarse grid tolerance: %g" % coarse_tol, "coarse grid iterations: %d" % coarse_iter,
+              "coarse grid restarts: %d" % coarse_restart, "print mode: 0", "method: %d" % method,
+              "mixed precision: %d" % mixed_precision, "randomize test vectors: 0",
+              "odd even preconditioning: %d" % odd_even, "kcycle: %d" % kcycle, "kcycle length: 5",
+              "kcycle restarts: 2", "kcycle tolerance: 1E-1", "interpolation: 2"]
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return path
+
+
+def read_conf(path, anti_pbc=True):
+    """Reference native configuration format (src/io.c:486-506): 4 x int32 [T,Z,Y,X], one double (plaquette), then
+    doubles [t][z][y][x][mu=T,Z,Y,X][3][3][re,im].  anti_pbc flips the time links of the last slice, which is what
+    the reference's reader does (io.c:535-541) and what dd_alpha_amg_set_conf expects from its caller."""
+    with open(path, "rb") as f:
+        dims = np.fromfile(f, dtype=np.int32, count=4)
+        plaq = float(np.fromfile(f, dtype=np.float64, count=1)[0])
+        n = int(np.prod(dims)) * 72
+        data = np.fromfile(f, dtype=np.float64, count=n)
+    U = data.reshape(tuple(int(d) for d in dims) + (4, 3, 3, 2)).copy()
+    if anti_pbc:
+        U[-1, :, :, :, 0] *= -1.0
+    return [int(d) for d in dims], plaq, U
+
+
+def random_gauge_field(lattice, seed=20261018, eps=0.3, anti_pbc=True):
+    """Deterministic synthetic SU(3) field U = exp(i eps H), H Gaussian traceless Hermitian (eps -> inf: "hot").
+    Shape [T][Z][Y][X][4][3][3][2] doubles, the reference's native order."""
+    rng = np.random.default_rng(seed)
+    shape = tuple(lattice) + (4,)
+    n = int(np.prod(shape))
+    out = np.empty((n, 3, 3), dtype=np.complex128)
+    chunk = 1 << 18
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        A = rng.standard_normal((b - a, 3, 3)) + 1j * rng.standard_normal((b - a, 3, 3))
+        H = 0.5 * (A + np.conj(np.swapaxes(A, 1, 2)))
+        H -= (np.trace(H, axis1=1, axis2=2) / 3.0)[:, None, None] * np.eye(3)
+        w, v = np.linalg.eigh(H)
+        out[a:b] = (v * np.exp(1j * eps * w)[:, None, :]) @ np.conj(np.swapaxes(v, 1, 2))
+    U = np.empty(shape + (3, 3, 2), dtype=np.float64)
+    U[..., 0] = out.real.reshape(shape + (3, 3))
+    U[..., 1] = out.imag.reshape(shape + (3, 3))
+    if anti_pbc:
+        U[-1, :, :, :, 0] *= -1.0
+    return U
+
+
+class DDalphaAMG:
+    """One live solver instance (the library keeps process-global state like the reference: one per process)."""
+
+    def __init__(self, lattice, block, m0=-0.5, csw=1.0, bc=2, setup_m0=None, lib=None, ini_path=None, **ini_kw):
+        self.L = load_library(lib)
+        self.lattice = [int(x) for x in lattice]
+        self.V = int(np.prod(self.lattice))
+        self._tmp = None
+        if ini_path is None:
+            self._tmp = tempfile.NamedTemporaryFile(suffix=".ini", delete=False)
+            self._tmp.close()
+            ini_path = write_ini(self._tmp.name, lattice, block, m0=m0, csw=csw, anti_pbc=1 if bc == 2 else 0, **ini_kw)
+        p = Par()
+        p.param_file_path = ini_path.encode()
+        LT, LZ, LY, LX = self.lattice
+        # the caller's layouts: native conf order / lexicographic spinors (offsets in doubles)
+        self._cf = CONF_INDEX_FCT(lambda t, z, y, x, mu: 18 * (4 * (x + LX * (y + LY * (z + LZ * t))) + mu))
+        self._vf = VECTOR_INDEX_FCT(lambda t, z, y, x: 24 * (x + LX * (y + LY * (z + LZ * t))))
+        self._gt = GLOBAL_TIME_FCT(lambda t: t)
+        # NULL index functions select the same default layouts inside the library without a Python callback per site
+        p.conf_index_fct = CONF_INDEX_FCT(0)
+        p.vector_index_fct = VECTOR_INDEX_FCT(0)
+        p.global_time = GLOBAL_TIME_FCT(0)
+        p.bc = bc
+        p.m0 = m0
+        p.csw = csw
+        p.setup_m0 = m0 if setup_m0 is None else setup_m0
+        self.L.dd_alpha_amg_init(p)
+        self.emulated = bool(self.L.dda_info(INFO.EMULATION, 0))
+
+    # ---- reference interface
+    def set_conf(self, U):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        assert U.size == self.V * 72
+        return self.L.dd_alpha_amg_set_conf(_dp(U))
+
+    def setup(self, iterations):
+        st = np.zeros(2, dtype=np.int32)
+        self.L.dd_alpha_amg_setup(int(iterations), _ip(st))
+        return st
+
+    def setup_update(self, iterations):
+        st = np.zeros(2, dtype=np.int32)
+        self.L.dd_alpha_amg_setup_update(int(iterations), _ip(st))
+        return st
+
+    def solve(self, b, tol=1e-10, scale_even=1.0, scale_odd=1.0, out=None):
+        b = np.ascontiguousarray(b, dtype=np.complex128)
+        x = np.zeros_like(b) if out is None else out
+        st = np.zeros(2, dtype=np.int32)
+        res = self.L.dd_alpha_amg_wilson_solve(_dp(x), _dp(b), tol, scale_even, scale_odd, _ip(st))
+        return x, res, st
+
+    def preconditioner(self, b):
+        b = np.ascontiguousarray(b, dtype=np.complex128)
+        x = np.zeros_like(b)
+        st = np.zeros(2, dtype=np.int32)
+        self.L.dd_alpha_amg_preconditioner(_dp(x), _dp(b), 1.0, 1.0, _ip(st))
+        return x
+
+    def free(self):
+        self.L.dd_alpha_amg_free()
+        if self._tmp is not None:
+            try:
+                os.unlink(self._tmp.name)
+            except OSError:
+                pass
+
+    # ---- operator-level entry points (include/dd_alpha_amg_b200.h)
+    def info(self, what, depth=0):
+        return self.L.dda_info(what, depth)
+
+    def set_option(self, what, value):
+        self.L.dda_set_option(what, float(value))
+
+    def stat(self, what):
+        return self.L.dda_get_stat(what)
+
+    def reset_stats(self):
+        self.L.dda_reset_stats()
+
+    def apply_dw(self, v, precision="double"):
+        v = np.ascontiguousarray(v, dtype=np.complex128)
+        out = np.zeros_like(v)
+        self.L.dda_apply_dw(0 if precision == "double" else 1, _dp(out), _dp(v))
+        return out
+
+    def operator_arrays(self):
+        D = np.zeros((self.V, 4, 3, 3), dtype=np.complex128)
+        cl = np.zeros((self.V, 42), dtype=np.complex128)
+        self.L.dda_get_operator(_dp(D), _dp(cl))
+        return D, cl
+
+    def level_shape(self, depth):
+        return self.info(INFO.SITES, depth), self.info(INFO.SITE_VARS, depth)
+
+    def set_interpolation(self, depth, P):
+        P = np.ascontiguousarray(P, dtype=np.complex64)
+        self.L.dda_set_interpolation(depth, _fp(P))
+
+    def get_interpolation(self, depth):
+        V, nc = self.level_shape(depth)
+        P = np.zeros((V * nc, self.info(INFO.TEST_VECTORS, depth)), dtype=np.complex64)
+        self.L.dda_get_interpolation(depth, _fp(P))
+        return P
+
+    def _level_op(self, op, depth, vin, out_depth, iparam=0, flag=0, out=None):
+        vin = np.ascontiguousarray(vin, dtype=np.complex64)
+        V, nc = self.level_shape(out_depth)
+        if out is None:
+            out = np.zeros(V * nc, dtype=np.complex64)
+        self.L.dda_level_op(op, depth, _fp(out), _fp(vin), iparam, flag)
+        return out
+
+    def level_apply(self, depth, v):
+        return self._level_op(OP.APPLY, depth, v, depth)
+
+    def restrict(self, depth, v):
+        return self._level_op(OP.RESTRICT, depth, v, depth + 1)
+
+    def interpolate(self, depth, vc):
+        return self._level_op(OP.INTERPOLATE, depth, vc, depth)
+
+    def smoother(self, depth, eta, n, phi0=None):
+        out = None if phi0 is None else np.ascontiguousarray(phi0, dtype=np.complex64).copy()
+        return self._level_op(OP.SMOOTHER, depth, eta, depth, iparam=n, flag=0 if phi0 is None else 1, out=out)
+
+    def vcycle(self, depth, eta):
+        return self._level_op(OP.VCYCLE, depth, eta, depth)
+
+    def coarsest_solve(self, b):
+        d = self.info(INFO.NUM_LEVELS) - 1
+        return self._level_op(OP.COARSEST_SOLVE, d, b, d)
+
+    def bench_op(self, op, depth=0, reps=10):
+        return self.L.dda_bench_op(op, depth, reps)
+
+    def solve_device(self, b, tol=1e-10):
+        b = np.ascontiguousarray(b, dtype=np.complex128)
+        self.L.dda_upload_source(_dp(b))
+        st = np.zeros(2, dtype=np.int32)
+        ms = np.zeros(1)
+        res = self.L.dda_solve_device(tol, _ip(st), _dp(ms))
+        return res, st, float(ms[0])
+
+    def download_solution(self):
+        x = np.zeros(self.V * 12, dtype=np.complex128)
+        self.L.dda_download_solution(_dp(x))
+        return x

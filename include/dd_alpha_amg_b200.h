@@ -1,0 +1,70 @@
+/* dd_alpha_amg_b200.h -- operator-level C entry points of libdd_alpha_amg.so (B200-native DDalphaAMG solve path).
+ *
+ * The reference exposes its hot-path operators only as internal C functions (no FFI); each entry point below is the
+ * C-ABI handle on the device implementation of one of them, so that tests can compare operator by operator with the
+ * reference and benchmarks can time one kernel family at a time.  Plain pointers and sizes only.
+ *
+ * Host-side vector conventions (identical to the reference's lexicographic order, data_layout.h:31-33):
+ *   fine double vectors : complex double [t][z][y][x][12]           (index 3*spin+colour)
+ *   level float vectors : complex float  [lexicographic site of the level][site vars]   (12 on the fine level,
+ *                         2*Nv below; first Nv = upper chirality)
+ * Everything is converted to the device-native order (aggregate -> Schwarz block -> even/odd, 32-site tiles)
+ * inside the library.
+ */
+#ifndef DD_ALPHA_AMG_B200_OPS_H
+#define DD_ALPHA_AMG_B200_OPS_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { DDA_DOUBLE = 0, DDA_FLOAT = 1 };
+enum { DDA_INFO_NUM_LEVELS = 0, DDA_INFO_SITES = 1, DDA_INFO_SITE_VARS = 2, DDA_INFO_TEST_VECTORS = 3,
+       DDA_INFO_BLOCK_SITES = 4, DDA_INFO_NUM_BLOCKS = 5, DDA_INFO_EMULATION = 6 };
+enum { DDA_OPT_USE_FAST = 0, DDA_OPT_PROFILE = 1, DDA_OPT_SEED = 2, DDA_OPT_PRINT = 3 };
+enum { DDA_STAT_LAUNCHES = 0, DDA_STAT_DEVICE_BYTES = 1, DDA_STAT_PLAQUETTE = 2, DDA_STAT_ITER = 3,
+       DDA_STAT_COARSE_ITER = 4, DDA_STAT_T_COARSEST = 5, DDA_STAT_T_RESTRICT = 6, DDA_STAT_T_INTERPOLATE = 7,
+       DDA_STAT_T_SMOOTH0 = 10, DDA_STAT_T_OP0 = 20 };
+enum { DDA_OP_APPLY = 0, DDA_OP_RESTRICT = 1, DDA_OP_INTERPOLATE = 2, DDA_OP_SMOOTHER = 3, DDA_OP_VCYCLE = 4,
+       DDA_OP_COARSEST_SOLVE = 5 };
+enum { DDA_BENCH_DW_DOUBLE = 0, DDA_BENCH_DW_FLOAT = 1, DDA_BENCH_LEVEL_APPLY = 2, DDA_BENCH_RESTRICT = 3,
+       DDA_BENCH_INTERPOLATE = 4, DDA_BENCH_SMOOTHER = 5, DDA_BENCH_VCYCLE = 6 };
+
+/* geometry of the hierarchy (reference: level_struct fields, main.h:263-341) */
+int dda_info(int what, int depth);
+void dda_set_option(int what, double value);
+double dda_get_stat(int what);
+void dda_reset_stats(void);
+
+/* eta = D_W phi on the fine level; reference: d_plus_clover_double / d_plus_clover_float (dirac_generic.c:159-277) */
+void dda_apply_dw(int precision, double *out_lex, const double *in_lex);
+/* operator arrays in the reference's formats: D[36*site+9*mu+3*r+c] = U/2 (dirac.c:80), clover[42*site+k]
+ * (dirac.c:386-398); lexicographic sites, complex double */
+void dda_get_operator(double *D_lex, double *clover_lex);
+
+/* prolongator of level `depth`, [lexicographic site][site var][Nv] complex float; reference:
+ * interpolation_PRECISION_struct.operator (interpolation_generic.c:74-90).  Setting it rebuilds the Galerkin coarse
+ * operators below (coarse_operator_PRECISION_setup, coarse_operator_generic.c:53-205). */
+void dda_set_interpolation(int depth, const float *P_lex);
+void dda_get_interpolation(int depth, float *P_lex);
+
+/* one hot-path operator of level `depth` on host vectors:
+ *  DDA_OP_APPLY          out = D in            apply_coarse_operator_PRECISION (coarse_operator_generic.c:383) / d_plus_clover_float
+ *  DDA_OP_RESTRICT       out(depth+1) = P^H in restrict_PRECISION (interpolation_generic.c:169)
+ *  DDA_OP_INTERPOLATE    out = P in(depth+1)   interpolate3_PRECISION (interpolation_generic.c:130)
+ *  DDA_OP_SMOOTHER       out = SAP(eta = in), iparam iterations, flag != 0: out holds the initial guess
+ *                                              smoother_PRECISION -> red_black_schwarz_PRECISION (schwarz_generic.c:1260)
+ *  DDA_OP_VCYCLE         out = one cycle applied to in   vcycle_PRECISION (vcycle_generic.c:91)
+ *  DDA_OP_COARSEST_SOLVE out = approximate D_c^-1 in     coarse_solve_odd_even_PRECISION (coarse_oddeven_generic.c:1139) */
+void dda_level_op(int op, int depth, float *out_lex, const float *in_lex, int iparam, int flag);
+
+/* device-resident timing (CUDA events on the launching stream), milliseconds per application */
+double dda_bench_op(int op, int depth, int reps);
+/* device-resident solve: upload once, solve (timed on the device), download */
+void dda_upload_source(const double *in_lex);
+double dda_solve_device(double tol, int *status, double *ms_out);
+void dda_download_solution(double *out_lex);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
