@@ -1,0 +1,122 @@
+// dw_kernel.cu -- hand-tuned full-lattice Wilson-Clover apply for sm_100a (double and float).
+//
+//   eta(x) = C(x) phi(x) - sum_mu [ (1-gamma_mu) D_mu(x) phi(x+mu) + (1+gamma_mu) D_mu(x-mu)^dagger phi(x-mu) ]
+// Reference counterpart: d_plus_clover_PRECISION (dirac_generic.c:159-277), which makes five passes over the volume
+// and materialises eight half-spinor fields; here it is ONE gather-form pass: every thread owns one site, reads its
+// 8 neighbours, 8 links and the clover block and writes the result once.
+//
+// Data layout (see common.cuh Lay): 32-site tiles, component-major inside a tile, so lane l of a warp reads
+// component c of site (tile*32 + l): every load instruction of a warp is one contiguous 256 B (float) / 512 B
+// (double) segment for the site's own data, and a permutation of at most a few such segments for neighbour data
+// (sites are ordered Schwarz-block-wise, even sites first, so neighbours of a tile live in few tiles).
+// Algorithmic traffic per site: 24 (phi) + 24 (eta) + 72 (4 links) + 72 (clover: 12 real diagonal + 30 complex) reals.
+#include "fine_op.h"
+#include "fine_op.cuh"
+
+namespace dda {
+
+#ifndef DDA_HOST_EMU
+
+template <class T> struct LdTraits;
+template <> struct LdTraits<float> { typedef float2 V; };
+template <> struct LdTraits<double> { typedef double2 V; };
+
+template <class T> __device__ __forceinline__ cx<T> ldc(const cx<T> *p) {
+  typedef typename LdTraits<T>::V V;
+  V v = __ldg(reinterpret_cast<const V *>(p));
+  return cx<T>(v.x, v.y);
+}
+
+template <int MU, class T>
+__device__ __forceinline__ void dw_hop_fwd(const cx<T> *__restrict__ D, const cx<T> *__restrict__ in, long tile_u, int lane, long n, cx<T> *out) {
+  // (1-gamma_mu) D_mu(x) phi(x+mu): link of the own site (coalesced), spinor of the +mu neighbour
+  const long nt = (n >> 5) * (12L << 5) + (n & 31);
+  cx<T> p[12], h[6], g[6], M[9];
+#pragma unroll
+  for (int c = 0; c < 12; c++) p[c] = ldc(in + nt + ((long)c << 5));
+#pragma unroll
+  for (int k = 0; k < 9; k++) M[k] = ldc(D + tile_u + ((long)(9 * MU + k) << 5) + lane);
+  project<MU, +1>(p, h);
+  su3_mul(M, h, g);
+  reconstruct_sub<MU, +1>(g, out);
+}
+
+template <int MU, class T>
+__device__ __forceinline__ void dw_hop_bwd(const cx<T> *__restrict__ D, const cx<T> *__restrict__ in, long n, cx<T> *out) {
+  // (1+gamma_mu) D_mu(x-mu)^dagger phi(x-mu): link and spinor of the -mu neighbour
+  const long nt = (n >> 5) * (12L << 5) + (n & 31);
+  const long nu = (n >> 5) * (36L << 5) + (n & 31);
+  cx<T> p[12], h[6], g[6], M[9];
+#pragma unroll
+  for (int c = 0; c < 12; c++) p[c] = ldc(in + nt + ((long)c << 5));
+#pragma unroll
+  for (int k = 0; k < 9; k++) M[k] = ldc(D + nu + ((long)(9 * MU + k) << 5));
+  project<MU, -1>(p, h);
+  su3_mul_dag(M, h, g);
+  reconstruct_sub<MU, -1>(g, out);
+}
+
+template <class T, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_dw_full(const cx<T> *__restrict__ D, const T *__restrict__ C, const int *__restrict__ nb, const cx<T> *__restrict__ in,
+          cx<T> *__restrict__ out, long V) {
+  const long s = blockIdx.x * (long)BLOCK + threadIdx.x;
+  if (s >= V) return;
+  const int lane = (int)(s & 31);
+  const long tile = s >> 5;
+  const long tile_s = tile * (12L << 5), tile_u = tile * (36L << 5), tile_c = tile * (72L << 5);
+  int n[8];
+#pragma unroll
+  for (int d = 0; d < 8; d++) n[d] = __ldg(nb + (long)d * V + s);
+
+  cx<T> r[12];
+  {
+    cx<T> x[12];
+#pragma unroll
+    for (int c = 0; c < 12; c++) x[c] = ldc(in + tile_s + ((long)c << 5) + lane);
+    // clover: two Hermitian 6x6 blocks, packed (site_clover_PRECISION, dirac_generic.h:723-799)
+    const T *Cs = C + tile_c + lane;
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) r[6 * b + i] = __ldg(Cs + ((long)(6 * b + i) << 5)) * x[6 * b + i];
+      int m = 0;
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = i + 1; j < 6; j++, m++) {
+          cx<T> cij(__ldg(Cs + ((long)(12 + 2 * (15 * b + m)) << 5)), __ldg(Cs + ((long)(12 + 2 * (15 * b + m) + 1) << 5)));
+          fma_(r[6 * b + i], cij, x[6 * b + j]);
+          fmac_(r[6 * b + j], cij, x[6 * b + i]);
+        }
+    }
+  }
+  dw_hop_fwd<0>(D, in, tile_u, lane, n[0], r);
+  dw_hop_bwd<0>(D, in, n[4], r);
+  dw_hop_fwd<1>(D, in, tile_u, lane, n[1], r);
+  dw_hop_bwd<1>(D, in, n[5], r);
+  dw_hop_fwd<2>(D, in, tile_u, lane, n[2], r);
+  dw_hop_bwd<2>(D, in, n[6], r);
+  dw_hop_fwd<3>(D, in, tile_u, lane, n[3], r);
+  dw_hop_bwd<3>(D, in, n[7], r);
+#pragma unroll
+  for (int c = 0; c < 12; c++) out[tile_s + ((long)c << 5) + lane] = r[c];
+}
+
+template <class T> void dw_apply_fast(const FineOp<T> &op, cx<T> *out, const cx<T> *in) {
+  DDA_ASSERT(op.sh == 5);
+  const int BLOCK = 128;
+  unsigned grid = (unsigned)((op.V + BLOCK - 1) / BLOCK);
+  if constexpr (sizeof(T) == 8) k_dw_full<T, BLOCK, 2><<<grid, BLOCK, 0, g_stream>>>(op.D, op.C, op.nb, in, out, op.V);
+  else k_dw_full<T, BLOCK, 4><<<grid, BLOCK, 0, g_stream>>>(op.D, op.C, op.nb, in, out, op.V);
+  g_launch_count++;
+#ifdef DDA_DEBUG_SYNC
+  CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());
+#endif
+}
+template void dw_apply_fast<float>(const FineOp<float> &, cf *, const cf *);
+template void dw_apply_fast<double>(const FineOp<double> &, cd *, const cd *);
+
+#endif
+
+}  // namespace dda

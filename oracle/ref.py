@@ -51,6 +51,8 @@ def load(flavour=""):
     L.ref_restrict.argtypes = [C.c_int, fp, fp]
     L.ref_interpolate.argtypes = [C.c_int, fp, fp]
     L.ref_smoother.argtypes = [C.c_int, fp, fp, C.c_int, C.c_int]
+    L.ref_coarsest_solve.argtypes = [fp, fp]; L.ref_coarsest_solve.restype = C.c_int
+    L.ref_vcycle.argtypes = [C.c_int, fp, fp]
     L.ref_plaquette.restype = C.c_double
     L.ref_norm_res.restype = C.c_double
     _LIB = L
@@ -227,6 +229,18 @@ class Reference:
         phi = np.zeros_like(eta) if phi0 is None else np.ascontiguousarray(phi0, dtype=np.complex64).copy()
         self.L.ref_smoother(depth, _fp(phi), _fp(eta), n, 0 if phi0 is None else 1)
         return phi
+
+    def coarsest_solve(self, b):
+        b = np.ascontiguousarray(b, dtype=np.complex64)
+        x = np.zeros_like(b)
+        it = self.L.ref_coarsest_solve(_fp(x), _fp(b))
+        return x, it
+
+    def vcycle(self, depth, eta):
+        eta = np.ascontiguousarray(eta, dtype=np.complex64)
+        out = np.zeros_like(eta)
+        self.L.ref_vcycle(depth, _fp(out), _fp(eta))
+        return out
 
     def free(self):
         self.L.ref_free()

@@ -86,7 +86,9 @@ double ref_solve_mt(double *out, double *in, double tol, int *status, double *se
   return g.norm_res;
 }
 
-void ref_free(void) { dd_alpha_amg_free(); }
+/* dd_alpha_amg_free (src/dd_alpha_amg.c:398) is only safe after a setup; without one the instance is abandoned
+ * (test infrastructure: the leak is accepted) */
+void ref_free(void) { if (g.setup_flag) dd_alpha_amg_free(); }
 
 /* what: 0 num_levels, 1 num inner sites(depth), 2 site vars(depth), 3 num_eig_vect(depth),
  *       4 vector_size incl. ghost shell(depth), 5 schwarz_vector_size, 6 num aggregates(depth), 7.. lattice dims */
@@ -191,16 +193,33 @@ void ref_get_interpolation(int depth, float *out) {
 
 /* coarse-level vectors at depth>=1 live in the level's native order; helpers to go from/to lexicographic.
  * intermediate levels: Schwarz order (s_float.op.translation_table); coarsest: lexicographic (identity). */
+/* native index of lexicographic site i: Schwarz order on intermediate levels; on the coarsest level with odd-even
+ * preconditioning the operator and all vectors are in even-then-odd order (src/gathering_generic.c:155-180) */
+static int *coarsest_eo_table(level_struct *lp) {
+  static int *tab = NULL; static int tabn = 0;
+  int *le = lp->local_lattice, ns = lp->num_inner_lattice_sites;
+  if (tab && tabn == ns) return tab;
+  if (tab) free(tab);
+  tab = (int*)malloc(sizeof(int)*ns); tabn = ns;
+  int i = 0;
+  for (int par = 0; par < 2; par++)
+    for (int t = 0; t < le[T]; t++) for (int z = 0; z < le[Z]; z++) for (int y = 0; y < le[Y]; y++) for (int x = 0; x < le[X]; x++)
+      if ((t+z+y+x)%2 == par) tab[x + le[X]*(y + le[Y]*(z + le[Z]*t))] = i++;
+  return tab;
+}
+static int native_index(level_struct *lp, int i) {
+  if (lp->level > 0) return lp->s_float.op.translation_table ? lp->s_float.op.translation_table[i] : i;
+  if (g.odd_even) return coarsest_eo_table(lp)[i];
+  return i;
+}
 static void lex_to_native(level_struct *lp, complex_float *dst, const float *src) {
   int nv = lp->num_lattice_site_var, ns = lp->num_inner_lattice_sites;
-  int *tt = lp->s_float.op.translation_table;
-  for (int i = 0; i < ns; i++) { int k = (lp->level > 0 && tt) ? tt[i] : i;
+  for (int i = 0; i < ns; i++) { int k = native_index(lp, i);
     for (int c = 0; c < nv; c++) dst[(size_t)k*nv+c] = src[2*((size_t)i*nv+c)] + I*src[2*((size_t)i*nv+c)+1]; }
 }
 static void native_to_lex(level_struct *lp, float *dst, const complex_float *src) {
   int nv = lp->num_lattice_site_var, ns = lp->num_inner_lattice_sites;
-  int *tt = lp->s_float.op.translation_table;
-  for (int i = 0; i < ns; i++) { int k = (lp->level > 0 && tt) ? tt[i] : i;
+  for (int i = 0; i < ns; i++) { int k = native_index(lp, i);
     for (int c = 0; c < nv; c++) { dst[2*((size_t)i*nv+c)] = crealf(src[(size_t)k*nv+c]); dst[2*((size_t)i*nv+c)+1] = cimagf(src[(size_t)k*nv+c]); } }
 }
 
@@ -210,7 +229,10 @@ void ref_coarse_apply(int depth, float *out, const float *in) {
   vector_float a = NULL, b = NULL;
   MALLOC(a, complex_float, lp->schwarz_vector_size); MALLOC(b, complex_float, lp->schwarz_vector_size);
   lex_to_native(lp, a, in);
-  apply_coarse_operator_float(b, a, &(lp->s_float.op), lp, no_threading);
+  /* coarsest level with odd-even: the full operator is only available through its even-odd factorisation
+   * (coarse_odd_even_PRECISION_test, src/coarse_oddeven_generic.c:1271-1319) */
+  if (lp->level == 0 && g.odd_even) coarse_odd_even_float_test(b, a, lp, no_threading);
+  else apply_coarse_operator_float(b, a, &(lp->s_float.op), lp, no_threading);
   native_to_lex(lp, out, b);
   FREE(a, complex_float, lp->schwarz_vector_size); FREE(b, complex_float, lp->schwarz_vector_size);
 }
@@ -263,6 +285,29 @@ void ref_smoother(int depth, float *phi_io, const float *eta, int n, int use_res
     for (int i = 0; i < l.num_inner_lattice_sites; i++) for (int c = 0; c < 12; c++) {
       phi_io[2*(12*(size_t)i+c)] = crealf(p[12*(size_t)tt[i]+c]); phi_io[2*(12*(size_t)i+c)+1] = cimagf(p[12*(size_t)tt[i]+c]); }
   } else native_to_lex(lp, phi_io, p);
+  FREE(p, complex_float, lp->schwarz_vector_size); FREE(e, complex_float, lp->schwarz_vector_size);
+}
+
+/* coarse_solve_odd_even_float (src/coarse_oddeven_generic.c:1139) on the coarsest level, lexicographic in/out;
+ * returns the number of GMRES iterations */
+int ref_coarsest_solve(float *x_out, const float *b_in) {
+  level_struct *lp = &l; while (lp->next_level) lp = lp->next_level;
+  int before = g.coarse_iter_count;
+  lex_to_native(lp, lp->p_float.b, b_in);
+  if (g.odd_even) coarse_solve_odd_even_float(&(lp->p_float), &(lp->oe_op_float), lp, no_threading);
+  else fgmres_float(&(lp->p_float), lp, no_threading);
+  native_to_lex(lp, x_out, lp->p_float.x);
+  return g.coarse_iter_count - before;
+}
+
+/* vcycle_float (src/vcycle_generic.c:91) at level `depth`, zero initial guess, lexicographic in/out */
+void ref_vcycle(int depth, float *phi_out, const float *eta) {
+  level_struct *lp = level_at(depth);
+  vector_float p = NULL, e = NULL;
+  MALLOC(p, complex_float, lp->schwarz_vector_size); MALLOC(e, complex_float, lp->schwarz_vector_size);
+  lex_to_native(lp, e, eta);
+  vcycle_float(p, NULL, e, _NO_RES, lp, no_threading);
+  native_to_lex(lp, phi_out, p);
   FREE(p, complex_float, lp->schwarz_vector_size); FREE(e, complex_float, lp->schwarz_vector_size);
 }
 
