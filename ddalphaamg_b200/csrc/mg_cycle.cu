@@ -70,11 +70,15 @@ static void block_mr_step(Level &L, const int *list, int nblk, int cnt, cf *lphi
 }
 
 void sap_fine_fast(Solver &s, cf *x, const cf *eta, int iters, bool zero_guess);
+bool sap_fine_fast_available(const Solver &s);
 
 void mg_smoother(Solver &s, int depth, cf *phi, const cf *eta, int iters, bool zero_guess) {
   Level &L = s.lev[depth];
   ProfScope ps(s, &s.t_smooth[depth]);
   const Geometry &g = L.geo;
+#ifndef DDA_HOST_EMU
+  if (depth == 0 && s.use_fast && sap_fine_fast_available(s)) { sap_fine_fast(s, phi, eta, iters, zero_guess); return; }
+#endif
   const int nc = g.nc, bs = g.bs, be = g.bs_even, bo = g.bs - g.bs_even;
   const long n = g.vlen();
   const int biter = s.p.block_iter[depth];
