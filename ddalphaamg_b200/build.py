@@ -57,7 +57,7 @@ def build(verbose=False):
     objs = _compile_all(srcs, objdir, lambda s, o: ["nvcc"] + flags + ["-c", s, "-o", o])
     if _newer(LIB, objs):
         subprocess.check_call(["nvcc", "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                                       "-Xcompiler", "-fopenmp", "-lcudart"])
+                                                                       "-Xcompiler", "-fopenmp", "-lcudart", "-lnccl"])
     return LIB
 
 

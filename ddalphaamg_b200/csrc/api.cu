@@ -2,6 +2,7 @@
 // reference by src/dd_alpha_amg.c:95-404) plus the operator-level entry points of include/dd_alpha_amg_b200.h that
 // tests and benchmarks use to reach individual hot-path operators.
 #include "solver.h"
+#include "halo.h"
 #include "../../include/dd_alpha_amg.h"
 #include "../../include/dd_alpha_amg_b200.h"
 #include <chrono>
@@ -32,6 +33,7 @@ void select_device() {
     fprintf(stderr, "dd_alpha_amg_b200: no CUDA device available (%s); this library has no CPU fallback\n", cudaGetErrorString(e));
     fatal("no GPU", __FILE__, __LINE__);
   }
+  if (g_comm.active() && g_stream) return;   // dda_comm_init already bound this process to its GPU
   const char *lr = getenv("DDA_DEVICE");
   if (!lr) lr = getenv("LOCAL_RANK");
   int dev = lr ? atoi(lr) % n : -1;
@@ -77,15 +79,9 @@ void init_common(dd_alpha_amg_par &p, bool from_struct) {
   s.p.csw = p.csw; s.p.m0 = p.m0; s.p.setup_m0 = p.setup_m0;
   if (p.bc == 2) s.p.anti_pbc = 1;
   params_finalize(s.p);
-  for (int m = 0; m < 4; m++) {
-    if (s.p.global_lattice[0][m] != s.p.local_lattice[0][m]) {
-      fprintf(stderr, "dd_alpha_amg_b200: global != local lattice needs the multi-GPU layer (dda_comm_init) -- not available in this build\n");
-      fatal("geometry", __FILE__, __LINE__);
-    }
-  }
   A->conf_index_fct = p.conf_index_fct; A->vector_index_fct = p.vector_index_fct; A->global_time = p.global_time;
   A->bc = p.bc;
-  s.seed = 20261018ULL;
+  s.seed = 20261018ULL + 7919ULL * (unsigned long long)g_comm.rank;
   solver_alloc_fine(s);
   A->initialised = true;
 }
@@ -152,6 +148,7 @@ double dd_alpha_amg_set_conf(double *gauge_field) {
     h2d(s.lexbuf, h.data(), sizeof(cd) * 36 * V);
     spinor_from_lex<double>(L0.geo, L0.Dd, s.lexbuf, 36);
     vscale(L0.Dd, L0.Dd, 0.5, V * 36);
+    halo_exchange<cd>(L0.geo, L0.Dd, 36, L0.geo.sh);
     solver_refresh_float_op(s);
   } else {
     solver_upload_conf(s, h.data());
@@ -304,6 +301,14 @@ double DDalphaAMG_solve(double *out, double *in, double tol, int *status) { retu
 void DDalphaAMG_finalize(void) { dd_alpha_amg_free(); }
 
 // ------------------------------------------------------------------------------------ operator-level entry points
+int dda_is_emulation(void) {
+#ifdef DDA_HOST_EMU
+  return 1;
+#else
+  return 0;
+#endif
+}
+
 int dda_info(int what, int depth) {
   need_init("dda_info");
   Solver &s = A->s;

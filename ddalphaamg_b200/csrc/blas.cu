@@ -1,9 +1,9 @@
 // blas.cu -- BLAS-1 + reductions (see blas.h)
 #include "blas.h"
+#include "comm.h"
 
 namespace dda {
 
-void (*g_allreduce_sum)(double *buf, int n) = nullptr;
 
 static const int MAXV = 64;
 template <class T> struct PtrArr { const cx<T> *p[MAXV]; };
@@ -57,8 +57,8 @@ template <class T> void vmulti_dot(cd *out, cx<T> *const *V, int m, const cx<T> 
     acc[1] += (double)a.re * b.im - (double)a.im * b.re;
   }, buf);
   double h[2 * MAXV];
+  comm_allreduce_sum(buf, 2 * m);
   d2h(h, buf, sizeof(double) * 2 * m);
-  if (g_allreduce_sum) g_allreduce_sum(h, 2 * m);
   for (int k = 0; k < m; k++) out[k] = cd(h[2 * k], h[2 * k + 1]);
 }
 
@@ -74,8 +74,8 @@ template <class T> void vmulti_dot_norm(cd *out, cx<T> *const *V, int m, const c
     acc[1] += (double)a.re * b.im - (double)a.im * b.re;
   }, buf);
   double h[2 * MAXV];
+  comm_allreduce_sum(buf, 2 * (m + 1));
   d2h(h, buf, sizeof(double) * 2 * (m + 1));
-  if (g_allreduce_sum) g_allreduce_sum(h, 2 * (m + 1));
   for (int k = 0; k <= m; k++) out[k] = cd(h[2 * k], h[2 * k + 1]);
 }
 
@@ -87,8 +87,8 @@ template <class T> cd vdot(const cx<T> *x, const cx<T> *y, long n) {
 template <class T> double vnorm2(const cx<T> *x, long n) {
   double *buf = red_buf();
   launch_reduce<1>(1, n, DLAMBDA(long seg, long i, double *acc) { (void)seg; cx<T> a = x[i]; acc[0] += (double)a.re * a.re + (double)a.im * a.im; }, buf);
+  comm_allreduce_sum(buf, 1);
   double h; d2h(&h, buf, sizeof(double));
-  if (g_allreduce_sum) g_allreduce_sum(&h, 1);
   return h;
 }
 

@@ -18,14 +18,13 @@ template <class T, class S> void vcast(cx<T> *y, const cx<S> *x, long n);       
 // y -= sum_k coef[k] V[k]   (coef on the host; k < m <= 64); reference vector_PRECISION_multi_saxpy
 template <class T> void vmulti_axpy(cx<T> *y, cx<T> *const *V, const cd *coef, int m, int sign, long n);
 
-// host-returning reductions (synchronise the stream); allreduce over ranks is applied inside when distributed
+// host-returning reductions (synchronise the stream); the sum over ranks (comm_allreduce_sum, NCCL) is applied to the
+// device buffer before the single device->host copy
 template <class T> cd vdot(const cx<T> *x, const cx<T> *y, long n);     // <x,y> = sum conj(x) y
 template <class T> double vnorm2(const cx<T> *x, long n);                 // sum |x|^2
 template <class T> void vmulti_dot(cd *out, cx<T> *const *V, int m, const cx<T> *w, long n);   // out[k] = <V[k], w>
 // fused: out[k] = <V[k], w> for k<m and out[m] = <w,w> in ONE launch + ONE device->host copy
 template <class T> void vmulti_dot_norm(cd *out, cx<T> *const *V, int m, const cx<T> *w, long n);
 
-// hook for multi-GPU global sums (set by the distributed layer; identity on one rank)
-extern void (*g_allreduce_sum)(double *buf, int n);
 
 }  // namespace dda

@@ -2,6 +2,7 @@
 // precision casts, clover-block inversion for the SAP Schur complement.
 #include "fine_op.h"
 #include "fine_op.cuh"
+#include "comm.h"
 
 namespace dda {
 
@@ -62,13 +63,14 @@ static HD M3 m3_mul_bd(const M3 &A, const M3 &B) { M3 C; for (int i = 0; i < 3; 
 static HD M3 m3_mul_ad(const M3 &A, const M3 &B) { M3 C; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { cd s(0.0, 0.0); for (int k = 0; k < 3; k++) fmac_(s, A.a[3 * k + i], B.a[3 * k + j]); C.a[3 * i + j] = s; } return C; }  // A^dag B
 static HD M3 m3_mul_adbd(const M3 &A, const M3 &B) { M3 C; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { cd s(0.0, 0.0); for (int k = 0; k < 3; k++) fma_(s, conj(A.a[3 * k + i]), conj(B.a[3 * j + k])); C.a[3 * i + j] = s; } return C; }  // A^dag B^dag
 
-struct CloverGeom { int L[4]; const int *lex2nat, *nat2lex; long V; int sh; };
-static HD long cg_site(const CloverGeom &g, const int *c, int d0, int s0, int d1, int s1) {
-  int q[4] = {c[0], c[1], c[2], c[3]};
-  if (d0 >= 0) q[d0] = (q[d0] + s0 + g.L[d0]) % g.L[d0];
-  if (d1 >= 0) q[d1] = (q[d1] + s1 + g.L[d1]) % g.L[d1];
-  long lx = q[3] + (long)g.L[3] * (q[2] + (long)g.L[2] * (q[1] + (long)g.L[1] * q[0]));
-  return g.lex2nat[lx];
+// neighbour-table walk: the shift along d1 (never a partitioned direction) is applied first, then the shift along d0
+// (may lead into a ghost slab, whose sites have no table entries of their own).  Only T (direction 0) is partitioned
+// and callers pass mu < nu as (d0, d1) = (mu, nu).
+struct CloverGeom { const int *nb; long V; int sh; };
+static HD long cg_site(const CloverGeom &g, long s, int d0, int s0, int d1, int s1) {
+  if (d1 >= 0) s = g.nb[(long)(s1 > 0 ? d1 : 4 + d1) * g.V + s];
+  if (d0 >= 0) s = g.nb[(long)(s0 > 0 ? d0 : 4 + d0) * g.V + s];
+  return s;
 }
 static HD M3 cg_link(const CloverGeom &g, const cd *D, long s, int mu) {
   const Lay lu = {36, g.sh};
@@ -87,8 +89,7 @@ static GammaTab gamma_tab() {
 }
 
 void fine_build_clover(const Geometry &geo, const cd *D, double *C, double m0, double csw, double *plaq_out) {
-  CloverGeom cg; for (int m = 0; m < 4; m++) cg.L[m] = geo.L[m];
-  cg.lex2nat = geo.d_lex2nat; cg.nat2lex = geo.d_nat2lex; cg.V = geo.V; cg.sh = geo.sh;
+  CloverGeom cg; cg.nb = geo.d_nb; cg.V = geo.V; cg.sh = geo.sh;
   const GammaTab gt = gamma_tab();
   const Lay lc = {72, geo.sh};
   double *d_plaq = dev_alloc<double>(1);
@@ -96,29 +97,26 @@ void fine_build_clover(const Geometry &geo, const cd *D, double *C, double m0, d
   // plaquette: sum_x sum_{mu<nu} Re tr U_mu(x) U_nu(x+mu) U_mu(x+nu)^dag U_nu(x)^dag / (6 V)   [0,3]
   launch_reduce<1>(1, V, DLAMBDA(long seg, long s, double *acc) {
     (void)seg;
-    long lx = cg.nat2lex[s]; int c[4];
-    c[3] = (int)(lx % cg.L[3]); lx /= cg.L[3]; c[2] = (int)(lx % cg.L[2]); lx /= cg.L[2]; c[1] = (int)(lx % cg.L[1]); c[0] = (int)(lx / cg.L[1]);
     double tr = 0;
     for (int mu = 0; mu < 4; mu++) for (int nu = mu + 1; nu < 4; nu++) {
-      M3 a = m3_mul(cg_link(cg, D, s, mu), cg_link(cg, D, cg_site(cg, c, mu, 1, -1, 0), nu));
-      M3 b = m3_mul_bd(a, cg_link(cg, D, cg_site(cg, c, nu, 1, -1, 0), mu));
+      M3 a = m3_mul(cg_link(cg, D, s, mu), cg_link(cg, D, cg_site(cg, s, mu, 1, -1, 0), nu));
+      M3 b = m3_mul_bd(a, cg_link(cg, D, cg_site(cg, s, nu, 1, -1, 0), mu));
       M3 p = m3_mul_bd(b, cg_link(cg, D, s, nu));
       tr += p.a[0].re + p.a[4].re + p.a[8].re;
     }
     acc[0] += 16.0 * tr;     // D = U/2
   }, d_plaq);
+  comm_allreduce_sum(d_plaq, 1);
   double h; d2h(&h, d_plaq, sizeof(double)); dev_free(d_plaq);
-  if (plaq_out) *plaq_out = h / (6.0 * (double)V);
+  if (plaq_out) *plaq_out = h / (6.0 * (double)V * (double)g_comm.size);
 
   launch_n(V, DLAMBDA(long s) {
-    long lx = cg.nat2lex[s]; int c[4];
-    c[3] = (int)(lx % cg.L[3]); lx /= cg.L[3]; c[2] = (int)(lx % cg.L[2]); lx /= cg.L[2]; c[1] = (int)(lx % cg.L[1]); c[0] = (int)(lx / cg.L[1]);
     cd blk[2][36];
     for (int b = 0; b < 2; b++) for (int k = 0; k < 36; k++) blk[b][k] = cd(0.0, 0.0);
     if (csw != 0.0) for (int mu = 0; mu < 4; mu++) for (int nu = mu + 1; nu < 4; nu++) {
-      long xpm = cg_site(cg, c, mu, 1, -1, 0), xpn = cg_site(cg, c, nu, 1, -1, 0);
-      long xmm = cg_site(cg, c, mu, -1, -1, 0), xmn = cg_site(cg, c, nu, -1, -1, 0);
-      long xpn_mm = cg_site(cg, c, nu, 1, mu, -1), xmm_mn = cg_site(cg, c, mu, -1, nu, -1), xmn_pm = cg_site(cg, c, nu, -1, mu, 1);
+      long xpm = cg_site(cg, s, mu, 1, -1, 0), xpn = cg_site(cg, s, nu, 1, -1, 0);
+      long xmm = cg_site(cg, s, mu, -1, -1, 0), xmn = cg_site(cg, s, nu, -1, -1, 0);
+      long xpn_mm = cg_site(cg, s, mu, -1, nu, 1), xmm_mn = cg_site(cg, s, mu, -1, nu, -1), xmn_pm = cg_site(cg, s, mu, 1, nu, -1);
       // leaf 1: U_mu(x) U_nu(x+mu) U_mu(x+nu)^dag U_nu(x)^dag
       M3 q = m3_mul_bd(m3_mul_bd(m3_mul(cg_link(cg, D, s, mu), cg_link(cg, D, xpm, nu)), cg_link(cg, D, xpn, mu)), cg_link(cg, D, s, nu));
       // leaf 2: U_nu(x) U_mu(x+nu-mu)^dag U_nu(x-mu)^dag U_mu(x-mu)
@@ -162,10 +160,11 @@ void fine_shift_clover(const Geometry &geo, double *C, double delta) {
 void fine_scale_clover(const Geometry &geo, double *C, double se, double so) {
   const Lay lc = {72, geo.sh};
   const int *n2l = geo.d_nat2lex; int L1 = geo.L[1], L2 = geo.L[2], L3 = geo.L[3];
+  const int poff = (geo.pc[0] * geo.L[0] + geo.pc[1] * geo.L[1] + geo.pc[2] * geo.L[2] + geo.pc[3] * geo.L[3]) & 1;
   launch_n(geo.V * 72, DLAMBDA(long i) {
     long s = i / 72; int k = (int)(i - 72 * s);
     long lx = n2l[s]; int x = (int)(lx % L3); lx /= L3; int y = (int)(lx % L2); lx /= L2; int z = (int)(lx % L1); int t = (int)(lx / L1);
-    C[lc.idx(s, k)] *= ((t + z + y + x) & 1) ? so : se;
+    C[lc.idx(s, k)] *= ((t + z + y + x + poff) & 1) ? so : se;
   });
 }
 

@@ -1,0 +1,37 @@
+// halo.cu -- see halo.h.  Pack kernel (gather the boundary slice into a contiguous face in the slab's own layout),
+// grouped send/recv with both neighbours of every partitioned direction, receive directly into the ghost slab.
+#include "halo.h"
+
+namespace dda {
+
+long g_halo_bytes = 0;
+
+template <class E> void halo_exchange(const Geometry &g, E *v, int nc, int sh) {
+  if (!g.partitioned()) return;
+  const Lay lay = {nc, sh};
+  for (int m = 0; m < 4; m++) {
+    if (g.P[m] <= 1) continue;
+    const long ns = g.slab[m];
+    const size_t bytes = sizeof(E) * (size_t)ns * nc;
+    E *b0 = (E *)comm_buffer(0, bytes), *b1 = (E *)comm_buffer(1, bytes);
+    const int *s0 = g.d_slice[m], *s1 = g.d_slice[4 + m];
+    launch_n(2 * ns * nc, DLAMBDA(long q) {
+      const long half = ns * nc;
+      const int side = q >= half; const long r = side ? q - half : q;
+      long i; int c; lay.decode(r, i, c);
+      const int *sl = side ? s1 : s0;
+      E *b = side ? b1 : b0;
+      b[r] = v[lay.idx(sl[i], c)];
+    });
+    // my x_m = 0 slice -> the -m neighbour's +m slab ; my x_m = L-1 slice -> the +m neighbour's -m slab
+    comm_group_begin();
+    comm_sendrecv(b0, v + g.gh_off[m] * nc, bytes, g.nbr_rank[4 + m], g.nbr_rank[m]);
+    comm_sendrecv(b1, v + g.gh_off[4 + m] * nc, bytes, g.nbr_rank[m], g.nbr_rank[4 + m]);
+    comm_group_end();
+    g_halo_bytes += 2 * (long)bytes;
+  }
+}
+template void halo_exchange<cf>(const Geometry &, cf *, int, int);
+template void halo_exchange<cd>(const Geometry &, cd *, int, int);
+
+}  // namespace dda

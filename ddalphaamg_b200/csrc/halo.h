@@ -1,0 +1,15 @@
+// halo.h -- ghost-slab exchange of a level's vectors / operator arrays (see lattice.h for the slab layout).
+// Reference counterparts: ghost_sendrecv_PRECISION / ghost_update_PRECISION (ghost_generic.c:171-414).
+#pragma once
+#include "common.cuh"
+#include "lattice.h"
+#include "comm.h"
+
+namespace dda {
+
+// fills the ghost slabs of `v` (E = element type, nc elements per site, layout Lay{nc, sh}) from the neighbour ranks.
+// No-op when the level is not partitioned.
+template <class E> void halo_exchange(const Geometry &g, E *v, int nc, int sh);
+extern long g_halo_bytes;   // bytes sent by this rank (statistics)
+
+}  // namespace dda

@@ -21,12 +21,14 @@ template <class T> struct Fgmres {
   int last_iter = 0;
   double last_relres = 0;
 
-  void alloc(long n_, int m_, int max_restart_, double tol_, bool flexible_) {
+  // n_: local vector length the solver works on; nalloc_ >= n_: allocated length (ghost slabs of a partitioned level)
+  void alloc(long n_, int m_, int max_restart_, double tol_, bool flexible_, long nalloc_ = 0) {
     release();
     n = n_; m = m_; max_restart = max_restart_; tol = tol_; flexible = flexible_;
-    V.resize(m + 1); for (auto &v : V) v = dev_alloc<C>(n);
-    if (flexible) { Z.resize(m); for (auto &z : Z) z = dev_alloc<C>(n); }
-    w = dev_alloc<C>(n); r = dev_alloc<C>(n);
+    const long na = nalloc_ > n_ ? nalloc_ : n_;
+    V.resize(m + 1); for (auto &v : V) v = dev_alloc<C>(na);
+    if (flexible) { Z.resize(m); for (auto &z : Z) z = dev_alloc<C>(na); }
+    w = dev_alloc<C>(na); r = dev_alloc<C>(na);
     H.assign((size_t)(m + 1) * m, cd(0, 0)); gamma.assign(m + 1, cd(0, 0)); c.assign(m, cd(0, 0)); s.assign(m, cd(0, 0)); y.assign(m, cd(0, 0));
     allocated = true;
   }

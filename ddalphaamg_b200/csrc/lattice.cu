@@ -36,14 +36,16 @@ void Geometry::build() {
   block_color.assign(nblocks, 0);
   std::vector<int> coord(4 * V);
   if (last && global_eo) {
+    const int poff = (pc[0] * L[0] + pc[1] * L[1] + pc[2] * L[2] + pc[3] * L[3]) & 1;   // parity of the rank's origin
     long ne = 0;
     for (int t = 0; t < L[0]; t++) for (int z = 0; z < L[1]; z++) for (int y = 0; y < L[2]; y++) for (int x = 0; x < L[3]; x++)
-      if (((t + z + y + x) & 1) == 0) ne++;
+      if (((t + z + y + x + poff) & 1) == 0) ne++;
     n_even = ne;
+    DDA_ASSERT(2 * ne == V);   // every rank holds the same number of even and odd sites
     long ce = 0, co = 0;
     for (int t = 0; t < L[0]; t++) for (int z = 0; z < L[1]; z++) for (int y = 0; y < L[2]; y++) for (int x = 0; x < L[3]; x++) {
       long i = lex(t, z, y, x);
-      long k = (((t + z + y + x) & 1) == 0) ? ce++ : ne + co++;
+      long k = (((t + z + y + x + poff) & 1) == 0) ? ce++ : ne + co++;
       lex2nat[i] = (int)k;
     }
   } else {
@@ -57,7 +59,7 @@ void Geometry::build() {
         ai = ai * na[m] + c[m] / Aq[m];
         bi = bi * nbpa[m] + (c[m] % Aq[m]) / Bq[m];
         li = li * Bq[m] + c[m] % Bq[m];
-        bsum += c[m] / Bq[m];
+        bsum += (pc[m] * L[m] + c[m]) / Bq[m];
       }
       long blk = ai * bpa + bi;
       lex2nat[lex(t, z, y, x)] = (int)(blk * bs + inblock[li]);
@@ -70,6 +72,32 @@ void Geometry::build() {
     nat2lex[k] = (int)i;
     coord[4 * (long)k + 0] = t; coord[4 * (long)k + 1] = z; coord[4 * (long)k + 2] = y; coord[4 * (long)k + 3] = x;
   }
+  // ghost slabs of the partitioned directions: slab-local index = rank of the site inside its slice in lexicographic order
+  Vg = 0;
+  std::vector<int> slice_rank[8];
+  std::vector<int> slices[8];
+  for (int m = 0; m < 4; m++) {
+    slab[m] = 0; gh_off[m] = gh_off[4 + m] = -1;
+    if (P[m] <= 1) continue;
+    slab[m] = V / L[m];
+    if (sh > 0) DDA_ASSERT(slab[m] % (1L << sh) == 0);
+    for (int side = 0; side < 2; side++) {
+      int d = side == 0 ? m : 4 + m;            // slices[m]: x_m = 0 ; slices[4+m]: x_m = L-1
+      int want = side == 0 ? 0 : L[m] - 1;
+      slice_rank[d].assign(V, -1);
+      // lexicographic order of the slice: identical on every rank (the native order of the coarsest level depends on
+      // the parity of the rank's origin)
+      for (long i = 0; i < V; i++) { long k = lex2nat[i]; if (coord[4 * k + m] == want) { slice_rank[d][k] = (int)slices[d].size(); slices[d].push_back((int)k); } }
+      DDA_ASSERT((long)slices[d].size() == slab[m]);
+    }
+    gh_off[m] = V + Vg; Vg += slab[m];
+    gh_off[4 + m] = V + Vg; Vg += slab[m];
+    int cp[4] = {pc[0], pc[1], pc[2], pc[3]}, cm[4] = {pc[0], pc[1], pc[2], pc[3]};
+    cp[m] = (pc[m] + 1) % P[m]; cm[m] = (pc[m] + P[m] - 1) % P[m];
+    nbr_rank[m] = ((cp[0] * P[1] + cp[1]) * P[2] + cp[2]) * P[3] + cp[3];
+    nbr_rank[4 + m] = ((cm[0] * P[1] + cm[1]) * P[2] + cm[2]) * P[3] + cm[3];
+  }
+  DDA_ASSERT(V + Vg < (1L << 31));
   h_nb.assign(8 * V, 0);
   std::vector<unsigned char> bf(V, 0), af(V, 0);
   for (long k = 0; k < V; k++) {
@@ -79,6 +107,12 @@ void Geometry::build() {
       cp[m] = (c[m] + 1) % L[m]; cm[m] = (c[m] + L[m] - 1) % L[m];
       h_nb[(long)m * V + k] = lex2nat[lex(cp[0], cp[1], cp[2], cp[3])];
       h_nb[(long)(4 + m) * V + k] = lex2nat[lex(cm[0], cm[1], cm[2], cm[3])];
+      if (P[m] > 1) {
+        // the periodic image inside the local lattice has the same transverse coordinates as the true neighbour on
+        // the adjacent rank: +mu ghost slab = neighbour's x_m = 0 slice, -mu slab = neighbour's x_m = L-1 slice
+        if (c[m] == L[m] - 1) h_nb[(long)m * V + k] = (int)(gh_off[m] + slice_rank[m][h_nb[(long)m * V + k]]);
+        if (c[m] == 0) h_nb[(long)(4 + m) * V + k] = (int)(gh_off[4 + m] + slice_rank[4 + m][h_nb[(long)(4 + m) * V + k]]);
+      }
       if (c[m] % Bq[m] == Bq[m] - 1) bf[k] |= (unsigned char)(1u << m);
       if (c[m] % Bq[m] == 0) bf[k] |= (unsigned char)(1u << (4 + m));
       if (c[m] % Aq[m] == Aq[m] - 1) af[k] |= (unsigned char)(1u << m);
@@ -88,6 +122,7 @@ void Geometry::build() {
   d_nb = dev_upload(h_nb);
   d_blkflag = dev_upload(bf);
   d_aggflag = dev_upload(af);
+  for (int d = 0; d < 8; d++) d_slice[d] = slices[d].empty() ? nullptr : dev_upload(slices[d]);
   d_lex2nat = dev_upload(lex2nat);
   d_nat2lex = dev_upload(nat2lex);
   std::vector<int> lists[2];
@@ -98,6 +133,7 @@ void Geometry::build() {
 void Geometry::destroy() {
   dev_free(d_nb); dev_free(d_blkflag); dev_free(d_aggflag); dev_free(d_lex2nat); dev_free(d_nat2lex);
   dev_free(d_blocklist[0]); dev_free(d_blocklist[1]); dev_free(d_agg2coarse);
+  for (int d = 0; d < 8; d++) { dev_free(d_slice[d]); d_slice[d] = nullptr; }
   d_nb = nullptr; d_blkflag = d_aggflag = nullptr; d_lex2nat = d_nat2lex = nullptr;
   d_blocklist[0] = d_blocklist[1] = nullptr; d_agg2coarse = nullptr;
 }

@@ -29,6 +29,16 @@ struct Geometry {
   int as = 0, nagg = 0;
   long n_even = 0;           // global_eo: number of even sites; block_eo: even sites per block (bs_even)
   int bs_even = 0;
+  // ---- domain decomposition (one process per GPU): process grid, this rank's coordinates, ghost slabs.
+  // Vector arrays of the level hold V local sites followed by Vg ghost sites: for every partitioned direction mu a
+  // +mu slab (copy of the +mu neighbour rank's x_mu = 0 slice) and a -mu slab (the -mu neighbour's x_mu = L-1 slice);
+  // the neighbour table points into the slabs.  Reference: ghost shell of data_layout.c:24-40, ghost_generic.c.
+  int P[4] = {1, 1, 1, 1}, pc[4] = {0, 0, 0, 0};
+  long Vg = 0;
+  long gh_off[8] = {-1, -1, -1, -1, -1, -1, -1, -1};   // first site index (>= V) of slab d (d<4: +mu, d>=4: -mu)
+  long slab[4] = {0, 0, 0, 0};
+  int nbr_rank[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int *d_slice[8] = {};                                 // d<4: local sites with x_mu = 0, d>=4: x_mu = L-1 (native order)
   std::vector<int> lex2nat, nat2lex, block_color;
   std::vector<int> h_nb;     // [8][V]
   // device tables
@@ -40,7 +50,9 @@ struct Geometry {
   int *d_agg2coarse = nullptr;         // aggregate index -> native site index on the next coarser level
 
   Lay lay() const { Lay l; l.nc = nc; l.sh = sh; return l; }
-  long vlen() const { return V * nc; }   // complex elements of a vector
+  long vlen() const { return V * nc; }   // complex elements of the local part of a vector
+  long valloc() const { return (V + Vg) * nc; }   // complex elements to allocate (local + ghost slabs)
+  bool partitioned() const { return Vg > 0; }
   bool coarsest() const { return A[0] == 0; }
   void build();
   void destroy();

@@ -8,6 +8,7 @@
 // (preconditioner.c:25-69), coarse_solve_odd_even / coarse_apply_schur_complement (coarse_oddeven_generic.c:1139-1189),
 // fgmres_PRECISION (linsolve_generic.c:219-413), wilson_driver (top_level.c:64-104).
 #include "solver.h"
+#include "halo.h"
 #include <chrono>
 
 namespace dda {
@@ -18,6 +19,8 @@ struct ProfScope {
   ProfScope(Solver &s_, double *a) : s(s_), acc(a), t0(0) { if (s.profile) { dev_sync(); t0 = now_s(); } }
   ~ProfScope() { if (s.profile) { dev_sync(); *acc += now_s() - t0; } }
 };
+
+void lv_halo(Level &L, const cf *v) { halo_exchange<cf>(L.geo, const_cast<cf *>(v), L.geo.nc, L.geo.sh); }
 
 void lv_apply(Level &L, cf *out, const cf *in, SiteSel sel, int hop, int dir, int self, int outmode, const cf *eta,
               const cf *in_self) {
@@ -31,6 +34,7 @@ void mg_apply_op(Solver &s, int depth, cf *out, const cf *in) {
   Level &L = s.lev[depth];
   ProfScope ps(s, &s.t_op[depth]);
   if (depth == 0) { solver_apply_dw<float>(s, out, in); return; }
+  lv_halo(L, in);
   lv_apply(L, out, in, sel_all(L.geo.V), HOP_ALL, 0, SELF_C, OUT_SET);
 }
 
@@ -100,6 +104,7 @@ void mg_smoother(Solver &s, int depth, cf *phi, const cf *eta, int iters, bool z
           r[q] = eta[q];
         });
       } else {
+        lv_halo(L, x);
         lv_apply(L, r, x, sb, HOP_ALL, 0, SELF_C, OUT_ETA_MINUS, eta);
       }
       if (eo) {
@@ -156,8 +161,10 @@ void mg_coarsest_schur(Solver &s, cf *out, const cf *in) {
   const Geometry &g = L.geo;
   long ne = g.n_even, no = g.V - g.n_even;
   cf *t0 = L.w[0], *t1 = L.w[1];
+  lv_halo(L, in);
   lv_apply(L, t0, in, sel_range(ne, no), HOP_ALL, 0, SELF_NONE, OUT_SET);                 // t0_o = N_oe in_e
   lv_apply(L, t1, t0, sel_range(ne, no), HOP_NONE, 0, SELF_CINV, OUT_NEG);                // t1_o = -Soo^-1 t0_o
+  lv_halo(L, t1);
   lv_apply(L, out, t1, sel_range(0, ne), HOP_ALL, 0, SELF_C, OUT_SET, nullptr, in);       // out_e = See in_e + N_eo t1_o
 }
 
@@ -174,10 +181,12 @@ void mg_coarsest_solve(Solver &s) {
   }
   // x_o = Soo^-1 b_o ; b_e <- b_e - H_eo x_o          (coarse_solve_odd_even, coarse_oddeven_generic.c:1139-1147)
   lv_apply(L, x, b, sel_range(ne, no), HOP_NONE, 0, SELF_CINV, OUT_SET);
+  lv_halo(L, x);
   lv_apply(L, t1, x, sel_range(0, ne), HOP_ALL, 0, SELF_NONE, OUT_ETA_MINUS, b);
   int it = L.kc.solve(x, t1, true);
   s.coarse_iter_count += it;
   // x_o = Soo^-1 (b_o - H_oe x_e)
+  lv_halo(L, x);
   lv_apply(L, t2, x, sel_range(ne, no), HOP_ALL, 0, SELF_NONE, OUT_ETA_MINUS, b);
   lv_apply(L, x, t2, sel_range(ne, no), HOP_NONE, 0, SELF_CINV, OUT_SET);
 }

@@ -6,6 +6,7 @@
 // (coarse_operator_generic.c:53-205), re_setup_PRECISION (setup_generic.c:278-321), inv_iter_inv_fcycle_PRECISION
 // (:441-503), gram_schmidt_PRECISION (linalg_generic.c:356-397), coarse_oddeven_setup (coarse_oddeven_generic.c:200-406).
 #include "solver.h"
+#include "halo.h"
 
 namespace dda {
 
@@ -42,18 +43,19 @@ void mg_alloc(Solver &s) {
         else { g.B[m] = 0; g.A[m] = 0; }
       }
       g.nc = 2 * s.lev[d - 1].nv; g.sh = 0; g.block_eo = false; g.global_eo = L.last && p.odd_even;
+      solver_process_grid(s, d, g);
       g.build();
       CoarseOp &c = L.cop;
       c.n = g.nc; c.V = g.V; c.n_even = L.last && p.odd_even ? g.n_even : g.V;
       long nn = (long)c.n * c.n;
-      c.F = dev_alloc<cf>(g.V * 4 * nn); c.S = dev_alloc<cf>(g.V * nn);
+      c.F = dev_alloc<cf>((g.V + g.Vg) * 4 * nn); c.S = dev_alloc<cf>(g.V * nn);   // hops of the ghost sites too
       c.Sinv = (L.last && p.odd_even) ? dev_alloc<cf>((g.V - c.n_even) * nn) : nullptr;
       c.nb = g.d_nb; c.blkflag = g.d_blkflag; c.aggflag = g.d_aggflag;
     }
   }
   for (int d = 0; d < s.nlev; d++) {
     Level &L = s.lev[d];
-    const long n = L.geo.vlen();
+    const long n = L.geo.valloc();
     if (!L.last) {
       Level &N = s.lev[d + 1];
       std::vector<int> a2c(L.geo.nagg);
@@ -71,13 +73,13 @@ void mg_alloc(Solver &s) {
     for (int i = 0; i < nw; i++) L.w[i] = dev_alloc<cf>(n);
     // Krylov wrappers
     if (d > 0 && !L.last) {
-      L.kc.alloc(n, p.kcycle_restart, p.kcycle_max_restart, p.kcycle_tol, true);
+      L.kc.alloc(L.geo.vlen(), p.kcycle_restart, p.kcycle_max_restart, p.kcycle_tol, true, n);
       Solver *sp = &s; int dd = d;
       L.kc.op = [sp, dd](cf *out, const cf *in) { mg_apply_op(*sp, dd, out, in); };
       L.kc.prec = [sp, dd](cf *out, const cf *in) { mg_vcycle(*sp, dd, out, in, true); };
     } else if (d > 0 && L.last) {
-      long nn = p.odd_even ? L.geo.n_even * L.geo.nc : n;
-      L.kc.alloc(nn, p.coarse_iter, p.coarse_restart, p.coarse_tol, false);
+      long nn = p.odd_even ? L.geo.n_even * L.geo.nc : L.geo.vlen();
+      L.kc.alloc(nn, p.coarse_iter, p.coarse_restart, p.coarse_tol, false, n);
       Solver *sp = &s; int dd = d;
       if (p.odd_even) L.kc.op = [sp](cf *out, const cf *in) { mg_coarsest_schur(*sp, out, in); };
       else L.kc.op = [sp, dd](cf *out, const cf *in) { mg_apply_op(*sp, dd, out, in); };
@@ -119,6 +121,7 @@ void mg_rebuild_coarse(Solver &s, int depth) {
   for (int j = 0; j < n; j++) {
     int ch = j / nv, k = j - ch * nv;
     tr_chirality_part(L.tr, w0, L.P[k], ch);
+    lv_halo(L, w0);
     lv_apply(L, w1, w0, all, HOP_INAGG, 0, SELF_C, OUT_SET);
     tr_restrict(L.tr, c.S, nn, (long)j * n, w1, L.tr_scratch);
     for (int mu = 0; mu < 4; mu++) {
@@ -126,6 +129,7 @@ void mg_rebuild_coarse(Solver &s, int depth) {
       tr_restrict(L.tr, c.F + mu * nn, 4 * nn, (long)j * n, w1, L.tr_scratch);
     }
   }
+  halo_exchange<cf>(N.geo, c.F, 4 * (int)nn, 0);     // forward hops of the -mu ghost sites (used by the backward hop)
   if (N.last && s.p.odd_even) coarse_invert_odd_self(c);
 }
 
@@ -224,7 +228,7 @@ void mg_setup(Solver &s, int setup_iters) {
   // outer solver
   {
     Solver *sp = &s;
-    s.outer.alloc(L0.geo.vlen(), p.restart, p.max_restart, p.tol, p.method > 0 && p.num_levels > 1);
+    s.outer.alloc(L0.geo.vlen(), p.restart, p.max_restart, p.tol, p.method > 0 && p.num_levels > 1, L0.geo.valloc());
     s.outer.op = [sp](cd *out, const cd *in) { solver_apply_dw<double>(*sp, out, in); };
     if (p.method > 0 && p.num_levels > 1) s.outer.prec = [sp](cd *out, const cd *in) { mg_preconditioner(*sp, out, in); };
     else s.outer.prec = nullptr;

@@ -20,6 +20,7 @@
 // x out.
 #include "solver.h"
 #include "fine_op.cuh"
+#include "halo.h"
 
 namespace dda {
 
@@ -276,7 +277,9 @@ void sap_fine_fast(Solver &s, cf *x, const cf *eta, int iters, bool zero_guess) 
     for (int col = 0; col < 2; col++) {
       const int nblk = g.nblk_color[col];
       if (nblk == 0) continue;
-      k_sap_fine<256><<<nblk, 128, smem, g_stream>>>(L.opf, x, eta, g.d_blocklist[col], biter, (zero_guess && cyc == 0 && col == 0) ? 1 : 0);
+      const int first = (zero_guess && cyc == 0 && col == 0) ? 1 : 0;
+      if (!first) halo_exchange<cf>(g, x, 12, g.sh);   // block residuals read x of neighbouring blocks on other ranks
+      k_sap_fine<256><<<nblk, 128, smem, g_stream>>>(L.opf, x, eta, g.d_blocklist[col], biter, first);
       g_launch_count++;
 #ifdef DDA_DEBUG_SYNC
       CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());

@@ -59,6 +59,7 @@ struct Solver {
 extern Solver *g_solver;
 
 // ---- fine operator management (solver_fine.cu)
+void solver_process_grid(Solver &s, int depth, Geometry &g);
 void solver_alloc_fine(Solver &s);
 void solver_free_fine(Solver &s);
 void solver_upload_conf(Solver &s, const double *gauge_lex);   // [site lex][mu][3][3][2] doubles (U, not U/2)
@@ -80,7 +81,9 @@ void mg_coarsest_solve(Solver &s);
 void mg_coarsest_schur(Solver &s, cf *out, const cf *in);   // even-site Schur complement of the coarsest operator
 void mg_apply_op(Solver &s, int depth, cf *out, const cf *in);  // full operator of the level (float)
 double mg_solve(Solver &s, cd *x, const cd *b, double tol, int *status);
-// generic operator dispatch of a level (float)
+// fills the ghost slabs of a level's float vector (no-op on an unpartitioned level)
+void lv_halo(Level &L, const cf *v);
+// generic operator dispatch of a level (float); hops that cross the rank boundary read the ghost slabs of `in`
 void lv_apply(Level &L, cf *out, const cf *in, SiteSel sel, int hop, int dir, int self, int outmode,
               const cf *eta = nullptr, const cf *in_self = nullptr);
 

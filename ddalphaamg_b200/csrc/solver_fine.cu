@@ -3,10 +3,28 @@
 // schwarz_PRECISION_setup (schwarz_generic.c:1037-1074, double -> float Schwarz-ordered copy),
 // schwarz_PRECISION_oddeven_setup (oddeven_generic.c:918-971), shift_update (dirac.c:669-691).
 #include "solver.h"
+#include "halo.h"
 
 namespace dda {
 
 Solver *g_solver = nullptr;
+
+// process grid of level `depth` from the parameters (global / local lattice); identical on all levels (no idle ranks);
+// rank -> grid coordinates with T slowest (the order MPI_Cart_create gives the reference, ghost.c:47-66)
+void solver_process_grid(Solver &s, int depth, Geometry &g) {
+  const Params &p = s.p;
+  long np = 1;
+  for (int m = 0; m < 4; m++) { g.P[m] = p.global_lattice[depth][m] / p.local_lattice[depth][m]; np *= g.P[m]; }
+  if (np != g_comm.size) {
+    fprintf(stderr, "dd_alpha_amg_b200: level %d process grid %d x %d x %d x %d needs %ld ranks, communicator has %d "
+            "(call dda_comm_init before dd_alpha_amg_init)\n", depth, g.P[0], g.P[1], g.P[2], g.P[3], np, g_comm.size);
+    fatal("geometry", __FILE__, __LINE__);
+  }
+  if (g.P[1] != 1 || g.P[2] != 1 || g.P[3] != 1) fatal("only the T direction can be partitioned in this build", __FILE__, __LINE__);
+  for (int m = 0; m < 4; m++) DDA_ASSERT(g.P[m] == p.global_lattice[0][m] / p.local_lattice[0][m]);
+  int r = g_comm.rank;
+  for (int m = 3; m >= 0; m--) { g.pc[m] = r % g.P[m]; r /= g.P[m]; }
+}
 
 void solver_alloc_fine(Solver &s) {
   DDA_ASSERT(!s.fine_alloc);
@@ -22,15 +40,17 @@ void solver_alloc_fine(Solver &s) {
     } else { g.B[m] = 0; g.A[m] = 0; }
   }
   g.nc = 12;
+  solver_process_grid(s, 0, g);
   long V = (long)g.L[0] * g.L[1] * g.L[2] * g.L[3];
   g.sh = (V % 32 == 0) ? 5 : 0;
   g.block_eo = (p.num_levels > 1);
   g.global_eo = false;
   g.build();
-  L.Dd = dev_alloc<cd>(V * 36); L.Cd = dev_alloc<double>(V * 72);
-  L.Df = dev_alloc<cf>(V * 36); L.Cf = dev_alloc<float>(V * 72); L.Cinvf = dev_alloc<float>(V * 72);
+  const long VA = V + g.Vg;     // local + ghost sites (links and vectors carry ghost slabs)
+  L.Dd = dev_alloc<cd>(VA * 36); L.Cd = dev_alloc<double>(V * 72);
+  L.Df = dev_alloc<cf>(VA * 36); L.Cf = dev_alloc<float>(V * 72); L.Cinvf = dev_alloc<float>(V * 72);
   s.lexbuf = dev_alloc<cd>(V * 36);
-  s.xb = dev_alloc<cd>(V * 12); s.xx = dev_alloc<cd>(V * 12);
+  s.xb = dev_alloc<cd>(VA * 12); s.xx = dev_alloc<cd>(VA * 12);
   L.opd.D = L.Dd; L.opd.C = L.Cd; L.opd.Cinv = nullptr; L.opd.nb = g.d_nb; L.opd.blkflag = g.d_blkflag; L.opd.aggflag = g.d_aggflag; L.opd.V = V; L.opd.sh = g.sh;
   L.opf.D = L.Df; L.opf.C = L.Cf; L.opf.Cinv = L.Cinvf; L.opf.nb = g.d_nb; L.opf.blkflag = g.d_blkflag; L.opf.aggflag = g.d_aggflag; L.opf.V = V; L.opf.sh = g.sh;
   s.fine_alloc = true;
@@ -52,6 +72,7 @@ void solver_upload_conf(Solver &s, const double *gauge_lex) {
   h2d(s.lexbuf, gauge_lex, sizeof(cd) * 36 * V);
   spinor_from_lex<double>(L.geo, L.Dd, s.lexbuf, 36);
   vscale(L.Dd, L.Dd, 0.5, V * 36);                       // reference stores D = U/2 (dirac.c:80)
+  halo_exchange<cd>(L.geo, L.Dd, 36, L.geo.sh);          // links of the ghost slabs (reference: dirac.c:405-496)
   fine_build_clover(L.geo, L.Dd, L.Cd, s.p.m0, s.p.csw, &s.plaq);
   s.m0_op = s.p.m0;
   solver_refresh_float_op(s);
@@ -61,7 +82,7 @@ void solver_upload_conf(Solver &s, const double *gauge_lex) {
 void solver_refresh_float_op(Solver &s) {
   Level &L = s.lev[0];
   long V = L.geo.V;
-  cast_links(L.Dd, L.Df, V * 36);
+  cast_links(L.Dd, L.Df, (V + L.geo.Vg) * 36);
   cast_reals(L.Cd, L.Cf, V * 72);
   double *tmp = dev_alloc<double>(V * 72);
   fine_invert_clover(L.geo, L.Cd, tmp);
@@ -88,6 +109,7 @@ void solver_sync_host_mirrors(Solver &s, bool to_device) {
   } else {
     h2d(s.lexbuf, s.h_gauge.data(), sizeof(cd) * 36 * V);
     spinor_from_lex<double>(L.geo, L.Dd, s.lexbuf, 36);
+    halo_exchange<cd>(L.geo, L.Dd, 36, L.geo.sh);
     for (long i = 0; i < V; i++) {
       for (int k = 0; k < 12; k++) c72[72 * i + k] = s.h_clover[84 * i + 2 * k];
       for (int k = 0; k < 60; k++) c72[72 * i + 12 + k] = s.h_clover[84 * i + 24 + k];
@@ -119,6 +141,7 @@ template <class T> void dw_apply_fast(const FineOp<T> &op, cx<T> *out, const cx<
 
 template <> void solver_apply_dw<double>(Solver &s, cd *out, const cd *in) {
   Level &L = s.lev[0];
+  halo_exchange<cd>(L.geo, const_cast<cd *>(in), 12, L.geo.sh);
 #ifndef DDA_HOST_EMU
   if (s.use_fast && L.geo.sh == 5) { dw_apply_fast<double>(L.opd, out, in); return; }
 #endif
@@ -126,6 +149,7 @@ template <> void solver_apply_dw<double>(Solver &s, cd *out, const cd *in) {
 }
 template <> void solver_apply_dw<float>(Solver &s, cf *out, const cf *in) {
   Level &L = s.lev[0];
+  halo_exchange<cf>(L.geo, const_cast<cf *>(in), 12, L.geo.sh);
 #ifndef DDA_HOST_EMU
   if (s.use_fast && L.geo.sh == 5) { dw_apply_fast<float>(L.opf, out, in); return; }
 #endif

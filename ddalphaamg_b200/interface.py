@@ -84,7 +84,12 @@ EXPORTS = ["dd_alpha_amg_init", "dd_alpha_amg_init_external_threading", "dd_alph
            "DDalphaAMG_finalize",
            "dda_info", "dda_set_option", "dda_get_stat", "dda_reset_stats", "dda_apply_dw", "dda_get_operator",
            "dda_set_interpolation", "dda_get_interpolation", "dda_level_op", "dda_bench_op", "dda_upload_source",
-           "dda_solve_device", "dda_download_solution"]
+           "dda_solve_device", "dda_download_solution",
+           "dda_comm_unique_id", "dda_comm_init", "dda_comm_finalize", "dda_comm_rank", "dda_comm_size",
+           "dda_comm_init_callbacks", "dda_is_emulation"]
+
+SENDRECV_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int)
+ALLREDUCE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int)
 
 
 def library_path():
@@ -134,8 +139,59 @@ def load_library(path=None):
     L.dda_solve_device.argtypes = [C.c_double, ip, dp]
     L.dda_solve_device.restype = C.c_double
     L.dda_download_solution.argtypes = [dp]
+    L.dda_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
+    L.dda_comm_unique_id.restype = C.c_int
+    L.dda_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int]
+    L.dda_comm_init_callbacks.argtypes = [C.c_int, C.c_int, SENDRECV_FN, ALLREDUCE_FN]
     _LIBS[path] = L
     return L
+
+
+_COMM_KEEPALIVE = []
+
+
+def comm_init(lib=None, device=None):
+    """Binds this process (one per GPU) into the library's communicator.  torch.distributed must be initialised: it
+    only carries the NCCL unique id from rank 0 to the others (what MPI_Bcast does for an MPI caller).  With the
+    host-emulation test library the exchanges themselves are delegated to torch.distributed (gloo)."""
+    import torch
+    import torch.distributed as dist
+    L = load_library(lib)
+    rank, size = dist.get_rank(), dist.get_world_size()
+    if L.dda_is_emulation():
+        def sendrecv(send, recv, nbytes, to, frm):
+            src = torch.frombuffer((C.c_char * nbytes).from_address(send), dtype=torch.uint8).clone()
+            dst = torch.empty(nbytes, dtype=torch.uint8)
+            if to == rank and frm == rank:
+                dst.copy_(src)
+            else:
+                reqs = [dist.isend(src, to), dist.irecv(dst, frm)]
+                for r in reqs:
+                    r.wait()
+            C.memmove(recv, dst.data_ptr(), nbytes)
+
+        def allreduce(buf, n):
+            t = torch.frombuffer((C.c_double * n).from_address(C.addressof(buf.contents)), dtype=torch.float64)
+            dist.all_reduce(t)
+
+        cbs = (SENDRECV_FN(sendrecv), ALLREDUCE_FN(allreduce))
+        _COMM_KEEPALIVE.append(cbs)
+        L.dda_comm_init_callbacks(rank, size, cbs[0], cbs[1])
+        return rank, size
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        n = L.dda_comm_unique_id(buf, 128)
+        assert n > 0
+    obj = [buf.raw if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", rank))
+    L.dda_comm_init(rank, size, obj[0], int(device))
+    return rank, size
+
+
+def comm_finalize(lib=None):
+    load_library(lib).dda_comm_finalize()
 
 
 def _dp(a):
@@ -168,7 +224,8 @@ def write_ini(path, lattice, block, levels=2, test_vectors=(20, 28), setup_iter=
                   "d%d setup iter: %d" % (d, setup_iter[min(d, len(setup_iter) - 1)])]
     if levels > 2:
         cl = coarse_lattice or [a // b for a, b in zip(lattice, block)]
-        lines += ["d1 global lattice: %d %d %d %d" % tuple(cl), "d1 local lattice: %d %d %d %d" % tuple(cl)]
+        cloc = [c * l // g for c, l, g in zip(cl, loc, lattice)]
+        lines += ["d1 global lattice: %d %d %d %d" % tuple(cl), "d1 local lattice: %d %d %d %d" % tuple(cloc)]
         if coarse_block is not None:
             lines += ["d1 block lattice: %d %d %d %d" % tuple(coarse_block)]
     lines += ["m0: %.16g" % m0, "csw: %.16g" % csw, "tolerance for relative residual: %g" % tol,
@@ -271,8 +328,11 @@ class DDalphaAMG:
     """One live solver instance (the library keeps process-global state like the reference: one per process)."""
 
     def __init__(self, lattice, block, m0=-0.5, csw=1.0, bc=2, setup_m0=None, lib=None, ini_path=None, **ini_kw):
+        """lattice: global lattice T,Z,Y,X; local_lattice (keyword): this rank's part (multi-GPU, after comm_init).
+        All host vectors of this object are the rank's LOCAL lexicographic parts."""
         self.L = load_library(lib)
-        self.lattice = [int(x) for x in lattice]
+        self.global_lattice = [int(x) for x in lattice]
+        self.lattice = [int(x) for x in (ini_kw.get("local_lattice") or lattice)]
         self.V = int(np.prod(self.lattice))
         self._tmp = None
         if ini_path is None:

@@ -31,6 +31,7 @@ enum { DDA_BENCH_DW_DOUBLE = 0, DDA_BENCH_DW_FLOAT = 1, DDA_BENCH_LEVEL_APPLY = 
 
 /* geometry of the hierarchy (reference: level_struct fields, main.h:263-341) */
 int dda_info(int what, int depth);
+int dda_is_emulation(void);   /* 1 only for the g++ host-emulation test build (tests/_emu), 0 for the CUDA library */
 void dda_set_option(int what, double value);
 double dda_get_stat(int what);
 void dda_reset_stats(void);
@@ -63,6 +64,20 @@ double dda_bench_op(int op, int depth, int reps);
 void dda_upload_source(const double *in_lex);
 double dda_solve_device(double tol, int *status, double *ms_out);
 void dda_download_solution(double *out_lex);
+
+/* ---- multi-GPU: one process per GPU, lattice partitioned along T ("d0 local lattice" != "d0 global lattice").
+ * Replaces the reference's MPI_COMM_WORLD / MPI_Cart_create plumbing (ghost.c:42-66); call before dd_alpha_amg_init.
+ * rank 0 creates the NCCL unique id (dda_comm_unique_id, <= 128 bytes), the launcher broadcasts it (MPI_Bcast,
+ * torch.distributed, a file ...) and every rank calls dda_comm_init(rank, size, id, cuda device or -1). */
+int dda_comm_unique_id(char *out, int len);
+void dda_comm_init(int rank, int size, const char *unique_id, int device);
+void dda_comm_finalize(void);
+int dda_comm_rank(void);
+int dda_comm_size(void);
+/* host-emulation (test) build only: exchanges are delegated to the test harness (torch.distributed / gloo) */
+typedef void (*dda_sendrecv_fn)(const void *send, void *recv, long bytes, int to, int from);
+typedef void (*dda_allreduce_fn)(double *buf, int n);
+void dda_comm_init_callbacks(int rank, int size, dda_sendrecv_fn sendrecv, dda_allreduce_fn allreduce);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,62 @@
+"""world_size-2 test of the multi-GPU path's host logic on CPU: lattice split along T over two processes (gloo),
+host-emulation build of the library, halo exchanges and global sums through torch.distributed; every rank checks its
+local part against the single-rank oracle (the operator is decomposition independent)."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+import parity_common as pc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def run_ranks(lib, backend, levels, tmp_path, world=2, timeout=900):
+    port = _free_port()
+    procs, outs = [], []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="4")
+        o = str(tmp_path / ("rank%d.json" % r))
+        outs.append(o)
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "multirank_worker.py"), lib, backend, o, str(levels)],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = []
+    for p in procs:
+        try:
+            logs.append(p.communicate(timeout=timeout)[0])
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+    for p, lg in zip(procs, logs):
+        assert p.returncode == 0, lg[-4000:]
+    return [json.load(open(o)) for o in outs]
+
+
+def check(results, imported_tol_iters=1):
+    for out in results:
+        assert out["plaq_err"] < 1e-12, out
+        assert out["dw_double"] <= pc.TOL_DOUBLE and out["dw_float"] <= pc.TOL_FLOAT, out
+        so = out["solve_own"]
+        assert so["iters"] > 0 and so["res"] < 1e-10 and so["res_ref_operator"] < 1.5e-10, out
+        assert abs(so["iters"] - so["ref_iters"]) <= 5, out
+        pc.assert_hierarchy(out["hierarchy"])
+        si = out["solve_imported"]
+        assert si["res"] < 1e-10 and abs(si["iters"] - si["ref_iters"]) <= imported_tol_iters, out
+
+
+@pytest.mark.parametrize("levels", [2, 3])
+def test_two_ranks_split_T(emu_lib, oracle_ref, tmp_path, levels):
+    check(run_ranks(emu_lib, "gloo", levels, tmp_path))
