@@ -35,8 +35,11 @@ WORKLOADS = {
     "16^3x32-L2": dict(lattice=[32, 16, 16, 16], levels=2, test_vectors=(20,), setup_iter=(3,), m0=-0.1,
                        config="configs[1]: 16^3x32 synthetic random SU(3) gauge field, 2-level AMG"),
     "32^3x64-L3": dict(lattice=[64, 32, 32, 32], levels=3, test_vectors=(20, 28), setup_iter=(3, 2), m0=-0.1,
+                       coarse_block=[2, 2, 2, 2],
                        config="configs[2]: 32^3x64 synthetic gauge field, 3-level AMG, mixed float/double"),
+    # level-1 blocks 3x2x2x2: the T extents 96 -> 24 -> 8 stay divisible by 8 ranks on every level (T-partition)
     "48^3x96-L3": dict(lattice=[96, 48, 48, 48], levels=3, test_vectors=(20, 28), setup_iter=(3, 2), m0=-0.1,
+                       coarse_block=[3, 2, 2, 2],
                        config="configs[3]: 48^3x96 synthetic gauge field, 3-level AMG"),
 }
 DEFAULT_WORKLOAD = "48^3x96-L3"
@@ -47,7 +50,7 @@ def solver_kwargs(w):
     kw = dict(levels=w["levels"], test_vectors=w["test_vectors"], setup_iter=w["setup_iter"], restart=10,
               max_restart=50, m0=w["m0"], csw=1.0, tol=1e-10, mixed_precision=1)
     if w["levels"] > 2:
-        kw["coarse_block"] = [2, 2, 2, 2]
+        kw["coarse_block"] = w.get("coarse_block", [2, 2, 2, 2])
     return kw
 
 
@@ -160,17 +163,38 @@ def run_native(args, w, name):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the library has no CPU fallback")
-    if world > 1:
-        raise RuntimeError("multi-GPU layer not built yet")
     torch.cuda.set_device(local_rank)
     os.environ["DDA_DEVICE"] = str(local_rank)
     lat = w["lattice"]
-    V = int(np.prod(lat))
     kw = solver_kwargs(w)
     peak, peak_src = peaks()
+    if world > 1:
+        # one process per GPU, lattice partitioned along T; torch.distributed only carries the NCCL id and the timing max
+        import torch.distributed as dist
+        from ddalphaamg_b200.interface import comm_init
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+        comm_init()
+        if lat[0] % world:
+            raise RuntimeError("T extent %d is not divisible by %d ranks" % (lat[0], world))
+        kw["local_lattice"] = [lat[0] // world] + lat[1:]
+    lt = lat[0] // world
+    V = int(np.prod(lat)) // world           # local sites
+    Vglob = int(np.prod(lat))
+
+    def rank_max(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
 
     t0 = time.time()
-    U = random_gauge_field(lat, seed=20261018, eps=0.3)
+    U = random_gauge_field(lat, seed=20261018, eps=0.3, t_range=(rank * lt, (rank + 1) * lt))
     t_gauge = time.time() - t0
     S = DDalphaAMG(lat, [4, 4, 4, 4], **kw)
     plaq = S.set_conf(U)
@@ -190,7 +214,7 @@ def run_native(args, w, name):
     clk = ClockSampler(local_rank)
     clk.start()
     S.reset_stats()
-    torch.cuda.synchronize()
+    barrier()
     torch.cuda.profiler.start()      # ncu --profile-from-start off: timed solves + operator benchmarks only
     tw0 = time.time()
     tot_ms, its = 0.0, None
@@ -198,8 +222,9 @@ def run_native(args, w, name):
         res, st, ms = S.solve_device(b)
         tot_ms += ms
         its = [int(st[0]), int(st[1])]
-    torch.cuda.synchronize()
-    wall = time.time() - tw0
+    barrier()
+    wall = rank_max(time.time() - tw0)
+    tot_ms = rank_max(tot_ms)        # device time (CUDA events on the library's stream), max over ranks
     launches = int(S.stat(STAT.LAUNCHES))
     clocks = clk.stop()
     if res > 1e-10 or its[0] < 0:
@@ -209,10 +234,12 @@ def run_native(args, w, name):
     # ---- end to end through the reference-facing C ABI, host buffers
     for _ in range(min(args.warmup, 2)):
         S.solve(b, out=x)
+    barrier()
     te = time.time()
     for _ in range(args.steps):
         _, res_e, st_e = S.solve(b, out=x)
-    e2e = (time.time() - te) / args.steps
+    barrier()
+    e2e = rank_max(time.time() - te) / args.steps
 
     # ---- operator throughput (CUDA events inside the library, device-resident)
     nlev = S.info(INFO.NUM_LEVELS)
@@ -220,6 +247,8 @@ def run_native(args, w, name):
     reps = 20
 
     def add(key, ms_, bytes_):
+        # per-rank algorithmic bytes of the local volume, slowest rank's time: GB/s and roofline fraction PER GPU
+        ms_ = rank_max(ms_)
         g = bytes_ / (ms_ * 1e-3) / 1e9
         ops[key] = {"ms": ms_, "algorithmic_bytes": bytes_, "gbs": g, "frac_of_peak": g / peak}
 
@@ -259,19 +288,26 @@ def run_native(args, w, name):
             "bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak,
             "traffic": None, "peak_source": peak_src}
 
+    if world > 1:
+        from ddalphaamg_b200.interface import comm_finalize
+        comm_finalize()
+        dist.barrier()
+        dist.destroy_process_group()
+
     out = {"metric": METRIC, "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * sec, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
            "dtype": "f64 outer / f32 cycle", "data": "synthetic",
-           "config": {"workload": name, "detail": w["config"], "lattice_TZYX": lat, "levels": w["levels"],
+           "config": {"workload": name, "detail": w["config"], "lattice_TZYX": lat, "local_lattice_TZYX": [lt] + lat[1:],
+                      "partition": "T split over %d GPU(s), NCCL send/recv halos + allreduce" % world, "levels": w["levels"],
                       "test_vectors": list(w["test_vectors"]), "m0": w["m0"], "csw": 1.0, "tol": 1e-10,
                       "gauge": "U=exp(i*0.3*H), H Gaussian traceless Hermitian, seed 20261018, plaquette %.6f" % plaq,
                       "l2": "working set %.1f GB per solve >> 126 MB L2 (inputs larger than L2, no flush)" % (dev_bytes / 1e9),
                       "iterations": its, "setup_seconds_untimed": t_setup},
-           "e2e": {"value": e2e, "unit": "s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * 16},
+           "e2e": {"value": e2e, "unit": "s", "h2d_bytes_per_step": n * 16 * world, "d2h_bytes_per_step": n * 16 * world},
            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "operators": ops,
            "time_share_seconds_profiled_solve": share, "wall_seconds_timed_region": wall}
 
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:
         try:
             csec, desc, cores, flavour, cits, dw, Vs = reference_solve_time(w["levels"], w, 3, 1)
             out["cpu_baseline"] = {"value": csec * V / Vs, "unit": "s", "cores": cores, "kind": "reference",

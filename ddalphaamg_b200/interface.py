@@ -294,32 +294,37 @@ def _gauge_chunk(args):
     return np.stack(R, axis=1).reshape(n, 3, 3)
 
 
-def random_gauge_field(lattice, seed=20261018, eps=0.3, anti_pbc=True):
+def random_gauge_field(lattice, seed=20261018, eps=0.3, anti_pbc=True, t_range=None):
     """Deterministic synthetic SU(3) field U = exp(i eps H), H Gaussian traceless Hermitian (eps -> inf: "hot").
     Shape [T][Z][Y][X][4][3][3][2] doubles, the reference's native order.  Chunks of 2^16 links carry independent
-    streams spawned from `seed` (same field for any thread count); chunks are generated by a thread pool."""
+    streams spawned from `seed` (same field for any thread count); chunks are generated by a thread pool.
+    t_range=(t0, t1): only the time slices [t0, t1) of the same global field (one rank's part)."""
     from concurrent.futures import ThreadPoolExecutor
-    shape = tuple(lattice) + (4,)
-    n = int(np.prod(shape))
+    T = int(lattice[0])
+    t0, t1 = (0, T) if t_range is None else (int(t_range[0]), int(t_range[1]))
+    per_t = int(np.prod(lattice[1:])) * 4
+    n = T * per_t
+    a0, a1 = t0 * per_t, t1 * per_t
     chunk = 1 << 16
     nch = (n + chunk - 1) // chunk
     seeds = np.random.SeedSequence(seed).spawn(nch)
     use_cuda = False
-    if n > (1 << 20):
+    if a1 - a0 > (1 << 20):
         try:
             import torch
             use_cuda = torch.cuda.is_available()
         except ImportError:
             pass
-    jobs = [(seeds[i], min(chunk, n - i * chunk), eps, use_cuda) for i in range(nch)]
-    U = np.empty((n, 3, 3, 2), dtype=np.float64)
+    c0, c1 = a0 // chunk, (a1 + chunk - 1) // chunk
+    jobs = [(seeds[i], min(chunk, n - i * chunk), eps, use_cuda) for i in range(c0, c1)]
+    U = np.empty((a1 - a0, 3, 3, 2), dtype=np.float64)
     with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
-        for i, blk in enumerate(ex.map(_gauge_chunk, jobs)):
-            a = i * chunk
-            U[a:a + blk.shape[0], :, :, 0] = blk.real
-            U[a:a + blk.shape[0], :, :, 1] = blk.imag
-    U = U.reshape(shape + (3, 3, 2))
-    if anti_pbc:
+        for i, blk in zip(range(c0, c1), ex.map(_gauge_chunk, jobs)):
+            lo, hi = max(a0, i * chunk), min(a1, i * chunk + blk.shape[0])
+            U[lo - a0:hi - a0, :, :, 0] = blk[lo - i * chunk:hi - i * chunk].real
+            U[lo - a0:hi - a0, :, :, 1] = blk[lo - i * chunk:hi - i * chunk].imag
+    U = U.reshape((t1 - t0,) + tuple(lattice[1:]) + (4, 3, 3, 2))
+    if anti_pbc and t1 == T:
         U[-1, :, :, :, 0] *= -1.0
     return U
 
