@@ -337,7 +337,7 @@ void dda_set_option(int what, double value) {
   need_init("dda_set_option");
   Solver &s = A->s;
   switch (what) {
-    case DDA_OPT_USE_FAST: s.use_fast = (int)value; break;
+    case DDA_OPT_USE_FAST: s.use_fast = (int)value; g_transfer_fast = (int)value; break;
     case DDA_OPT_PROFILE: s.profile = (int)value; break;
     case DDA_OPT_SEED: s.seed = (unsigned long long)value; break;
     case DDA_OPT_PRINT: s.p.print = (int)value; break;

@@ -10,14 +10,15 @@
 //   e_o = Doo^-1 r_o ; t_e = r_e - Deo e_o
 //   block_iter x minimal residual on the even-odd Schur complement S = Dee - Deo Doo^-1 Doe
 //   e_o = Doo^-1 (r_o - Doe e_e) ; x += e
-// is one kernel: the block's links (73.7 KB in float) live in shared memory for the whole visit, the iteration
-// vectors live in registers (each thread owns one even and one odd site of the block, so every thread is busy in
-// both half steps), and only the vector that the opposite parity has to gather is exchanged through a 24.6 KB shared
-// buffer.  Clover blocks (even sites) and their inverses (odd sites) are streamed from L2.  Inner products of the MR
-// step are warp-shuffle + one shared-memory stage.  98.5 KB shared memory per CTA -> 2 CTAs per SM.
-//
-// HBM traffic per block visit (algorithmic): links 256*288 B + clover/inverse 256*288 B (+L2 re-reads) + x, eta in,
-// x out.
+// is one kernel.  The block's links (73.7 KB in float) stay in shared memory for the whole visit; the iteration
+// vectors stay in registers; only the vector that the opposite parity has to gather goes through a 24.6 KB shared
+// buffer.  Work decomposition: a PAIR of threads (lanes l and l^16) owns one even and one odd site of the block;
+// thread s of the pair owns spin components {s, 2+s} of both sites, i.e. half of every half-spinor projection,
+// SU(3) multiply and clover row block -- same instruction stream for both (the gamma-matrix signs that differ
+// between the halves are a per-thread +-1 factor), halves recombined with 6 warp shuffles per operator.  This gives
+// 8 warps per block visit and 16 warps per SM at <= 128 registers (the one-thread-per-site-pair variant ran at 7
+// warps/SM and 21 % issue utilisation, see profiles/).  Clover blocks (even sites) and their inverses (odd sites) are
+// streamed from L2.  MR inner products: warp shuffle + one shared-memory stage.  98.6 KB shared memory -> 2 CTAs/SM.
 #include "solver.h"
 #include "fine_op.cuh"
 #include "halo.h"
@@ -26,235 +27,371 @@ namespace dda {
 
 #ifndef DDA_HOST_EMU
 
-template <int BS> struct SapShared {
-  float2 U[36][BS];         // links of the block's sites, [9*mu + 3*row + col][site]
-  float2 Vb[12][BS];        // exchange buffer: [component][site in block]
-  float red[2][BS / 64][4];
+namespace sap {
+
+const int BS = 256;                 // sites per block (4^4), BS threads per CTA
+struct Shared {
+  float2 U[36][BS];                 // links of the block's sites, [9*mu + 3*row + col][site]
+  float2 Vb[12][BS];                // exchange buffer [component][site in block]
+  float red[2][BS / 32][4];
+};
+
+struct Ctx {                        // per-thread constants of the pair decomposition
+  int s;                            // which half: owns spins s and 2+s
+  float sg;                         // s ? +1 : -1
+  int up, loA, loB;                 // component offsets: 3s, 6+3s (own lower spin), 6+3(1-s) (partner's lower spin)
 };
 
 __device__ __forceinline__ cf ld2(const float2 &v) { return cf(v.x, v.y); }
 
-// hop part of the block operator restricted to in-block neighbours, gather form, operands in shared memory:
-//   out -= (1-gamma_mu) D_mu(x) v(x+mu) + (1+gamma_mu) D_mu(x-mu)^dagger v(x-mu)
-template <int MU, int BS>
-__device__ __forceinline__ void sm_hop_pair(const SapShared<BS> &sm, int l, unsigned inmask, unsigned nbf, unsigned nbb, cf *out) {
+// ------------------------------------------------------------------------------------------------------------------
+// CODE SIZE matters here: with every operator application inlined at its call site the visit is ~17 k instructions
+// (270 KB) and the kernel stalls on instruction fetch (ncu: 55 % of the samples "no instruction",
+// profiles/r1_ncu_full_k_sap_fine_a.txt).  The visit is therefore written as loops in which each operator (in-block
+// hops for the odd / even site, clover, clover inverse) appears exactly ONCE: k_sap_fine's main loop below, and a
+// two-pass loop with register rotation for the residual of the pair's two sites.
+//
+// Half hop for the thread owning spins {s, 2+s} (sg = s ? 1 : -1), S = +1 forward / -1 backward:
+//   h = pu - S u pl ,  g = W h ,  up -= g ,  low += S u' g ,   W = D_mu(x) or D_mu(x-mu)^dagger
+//   T: u = -1,    pl = spin 2+s, u' = -1     -> lowA        Z: u = -i,   pl = spin 3-s, u' = +i     -> lowB
+//   X: u = sg i,  pl = spin 2+s, u' = -sg i  -> lowA        Y: u = sg,   pl = spin 3-s, u' = sg     -> lowB
+// (gamma basis BASIS0, clifford.h:39-100; same arithmetic as project / reconstruct_sub in fine_op.cuh).  lowA is the
+// thread's own lower spin, lowB the partner's (handed over by shuffle in pair_combine).
+
+// one half of a hop with compile-time direction MU and sign S (+1 forward, -1 backward)
+template <int MU, int S>
+__device__ __forceinline__ void half_hop(const cf *pu, const cf *pl, const cf *M, float sg, cf *up, cf *lowA, cf *lowB) {
+  cf h[3], g[3];
+  const float t = (S > 0) ? sg : -sg;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    if (MU == 0) h[c] = (S > 0) ? pu[c] + pl[c] : pu[c] - pl[c];
+    else if (MU == 1) h[c] = (S > 0) ? cf(pu[c].re - pl[c].im, pu[c].im + pl[c].re) : cf(pu[c].re + pl[c].im, pu[c].im - pl[c].re);
+    else if (MU == 2) h[c] = cf(pu[c].re - t * pl[c].re, pu[c].im - t * pl[c].im);
+    else h[c] = cf(pu[c].re + t * pl[c].im, pu[c].im - t * pl[c].re);
+  }
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    cf a(0.f, 0.f);
+    if (S > 0) { a = M[3 * r] * h[0]; fma_(a, M[3 * r + 1], h[1]); fma_(a, M[3 * r + 2], h[2]); }
+    else { fmac_(a, M[r], h[0]); fmac_(a, M[3 + r], h[1]); fmac_(a, M[6 + r], h[2]); }
+    g[r] = a;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    up[c] -= g[c];
+    if (MU == 0) { if (S > 0) lowA[c] -= g[c]; else lowA[c] += g[c]; }
+    else if (MU == 1) { if (S > 0) { lowB[c].re -= g[c].im; lowB[c].im += g[c].re; } else { lowB[c].re += g[c].im; lowB[c].im -= g[c].re; } }
+    else if (MU == 2) { lowB[c].re += t * g[c].re; lowB[c].im += t * g[c].im; }
+    else { lowA[c].re += t * g[c].im; lowA[c].im -= t * g[c].re; }
+  }
+}
+
+// in-block hop pair of direction MU, operands in shared memory (gather form); vu / vl: the thread's component rows
+template <int MU>
+__device__ __forceinline__ void sm_hop_pair(const Shared &sm, const float2 *vu, const float2 *vl, float sg, int l, unsigned inmask,
+                                            unsigned nbf, unsigned nbb, cf *up, cf *lowA, cf *lowB) {
   if (inmask & (1u << MU)) {
     const int n = (nbf >> (8 * MU)) & 0xFF;
-    cf p[12], h[6], g[6], M[9];
+    cf pu[3], pl[3], M[9];
 #pragma unroll
-    for (int c = 0; c < 12; c++) p[c] = ld2(sm.Vb[c][n]);
+    for (int c = 0; c < 3; c++) { pu[c] = ld2(vu[c * BS + n]); pl[c] = ld2(vl[c * BS + n]); }
 #pragma unroll
     for (int k = 0; k < 9; k++) M[k] = ld2(sm.U[9 * MU + k][l]);
-    project<MU, +1>(p, h);
-    su3_mul(M, h, g);
-    reconstruct_sub<MU, +1>(g, out);
+    half_hop<MU, +1>(pu, pl, M, sg, up, lowA, lowB);
   }
   if (inmask & (1u << (4 + MU))) {
     const int n = (nbb >> (8 * MU)) & 0xFF;
-    cf p[12], h[6], g[6], M[9];
+    cf pu[3], pl[3], M[9];
 #pragma unroll
-    for (int c = 0; c < 12; c++) p[c] = ld2(sm.Vb[c][n]);
+    for (int c = 0; c < 3; c++) { pu[c] = ld2(vu[c * BS + n]); pl[c] = ld2(vl[c * BS + n]); }
 #pragma unroll
     for (int k = 0; k < 9; k++) M[k] = ld2(sm.U[9 * MU + k][n]);
-    project<MU, -1>(p, h);
-    su3_mul_dag(M, h, g);
-    reconstruct_sub<MU, -1>(g, out);
+    half_hop<MU, -1>(pu, pl, M, sg, up, lowA, lowB);
   }
 }
-template <int BS>
-__device__ __forceinline__ void sm_hops(const SapShared<BS> &sm, int l, unsigned inmask, unsigned nbf, unsigned nbb, cf *out) {
-  sm_hop_pair<0, BS>(sm, l, inmask, nbf, nbb, out);
-  sm_hop_pair<1, BS>(sm, l, inmask, nbf, nbb, out);
-  sm_hop_pair<2, BS>(sm, l, inmask, nbf, nbb, out);
-  sm_hop_pair<3, BS>(sm, l, inmask, nbf, nbb, out);
+
+// hop pair to neighbouring blocks, operands in global memory (tiled layout), only directions flagged in `mask`
+template <int MU>
+__device__ __forceinline__ void gl_hop_pair(const FineOp<float> &op, const Ctx &cx_, long s, unsigned mask, const cf *x,
+                                            cf *up, cf *lowA, cf *lowB) {
+  const int lo = (MU == 0 || MU == 3) ? cx_.loA : cx_.loB;
+  if (mask & (1u << MU)) {
+    const long n = op.nb[(long)MU * op.V + s];
+    const long nv = (n >> 5) * (12L << 5) + (n & 31), su = (s >> 5) * (36L << 5) + (s & 31);
+    cf pu[3], pl[3], M[9];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { pu[c] = x[nv + ((long)(cx_.up + c) << 5)]; pl[c] = x[nv + ((long)(lo + c) << 5)]; }
+#pragma unroll
+    for (int k = 0; k < 9; k++) M[k] = op.D[su + ((long)(9 * MU + k) << 5)];
+    half_hop<MU, +1>(pu, pl, M, cx_.sg, up, lowA, lowB);
+  }
+  if (mask & (1u << (4 + MU))) {
+    const long n = op.nb[(long)(4 + MU) * op.V + s];
+    const long nv = (n >> 5) * (12L << 5) + (n & 31), nu = (n >> 5) * (36L << 5) + (n & 31);
+    cf pu[3], pl[3], M[9];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { pu[c] = x[nv + ((long)(cx_.up + c) << 5)]; pl[c] = x[nv + ((long)(lo + c) << 5)]; }
+#pragma unroll
+    for (int k = 0; k < 9; k++) M[k] = op.D[nu + ((long)(9 * MU + k) << 5)];
+    half_hop<MU, -1>(pu, pl, M, cx_.sg, up, lowA, lowB);
+  }
 }
 
-template <int BS>
-__device__ __forceinline__ void put(SapShared<BS> &sm, int l, const cf *v) {
+// combine the pair's partial results: y[0..2] = spin s, y[3..5] = spin 2+s of N v (own lowA + partner's lowB)
+__device__ __forceinline__ void pair_combine(const cf *up, const cf *lowA, const cf *lowB, cf *y) {
 #pragma unroll
-  for (int c = 0; c < 12; c++) sm.Vb[c][l] = make_float2(v[c].re, v[c].im);
+  for (int c = 0; c < 3; c++) {
+    const float pr = __shfl_xor_sync(0xffffffffu, lowB[c].re, 16), pi = __shfl_xor_sync(0xffffffffu, lowB[c].im, 16);
+    y[c] = up[c];
+    y[3 + c] = cf(lowA[c].re + pr, lowA[c].im + pi);
+  }
 }
 
-// site-local packed Hermitian 2x(6x6) multiply from global memory (tiled layout), y = M x
-__device__ __forceinline__ void clov(const float *__restrict__ C, long tile_c, int lane, const cf *x, cf *y) {
-  const float *Cs = C + tile_c + lane;
+// y = N v for site l of the block (in-block hops only); v is in the shared exchange buffer
+__device__ __forceinline__ void sm_hops(const Shared &sm, const Ctx &cx_, int l, unsigned inmask, unsigned nbf, unsigned nbb, cf *y) {
+  cf up[3], lowA[3], lowB[3];
 #pragma unroll
+  for (int c = 0; c < 3; c++) { up[c] = cf(0.f, 0.f); lowA[c] = cf(0.f, 0.f); lowB[c] = cf(0.f, 0.f); }
+  const float2 *vu = &sm.Vb[cx_.up][0], *va = &sm.Vb[cx_.loA][0], *vb = &sm.Vb[cx_.loB][0];
+  sm_hop_pair<0>(sm, vu, va, cx_.sg, l, inmask, nbf, nbb, up, lowA, lowB);
+  sm_hop_pair<1>(sm, vu, vb, cx_.sg, l, inmask, nbf, nbb, up, lowA, lowB);
+  sm_hop_pair<2>(sm, vu, vb, cx_.sg, l, inmask, nbf, nbb, up, lowA, lowB);
+  sm_hop_pair<3>(sm, vu, va, cx_.sg, l, inmask, nbf, nbb, up, lowA, lowB);
+  pair_combine(up, lowA, lowB, y);
+}
+
+// y = N x restricted to the hops that leave the block (flags in `mask`), operands in global memory
+__device__ __forceinline__ void gl_hops(const FineOp<float> &op, const Ctx &cx_, long s, unsigned mask, const cf *x, cf *y) {
+  cf up[3], lowA[3], lowB[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) { up[c] = cf(0.f, 0.f); lowA[c] = cf(0.f, 0.f); lowB[c] = cf(0.f, 0.f); }
+  if (mask) {
+    gl_hop_pair<0>(op, cx_, s, mask, x, up, lowA, lowB); gl_hop_pair<1>(op, cx_, s, mask, x, up, lowA, lowB);
+    gl_hop_pair<2>(op, cx_, s, mask, x, up, lowA, lowB); gl_hop_pair<3>(op, cx_, s, mask, x, up, lowA, lowB);
+  }
+  pair_combine(up, lowA, lowB, y);
+}
+
+__device__ __forceinline__ void put(Shared &sm, const Ctx &cx_, int l, const cf *v) {
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    sm.Vb[cx_.up + c][l] = make_float2(v[c].re, v[c].im);
+    sm.Vb[cx_.loA + c][l] = make_float2(v[3 + c].re, v[3 + c].im);
+  }
+}
+
+// index of the packed upper-triangle entry (r, c), r < c, of a Hermitian 6x6 block (row-major over r < c)
+__host__ __device__ constexpr int tri(int r, int c) { return r * 6 - r * (r + 1) / 2 + (c - r - 1); }
+
+// own half of y = M x for the packed Hermitian 2 x (6x6) site matrix at Cs (pointer already offset by tile and lane):
+// x, y hold the own components (spin s, spin 2+s); the partner's components come by shuffle.  Thread s computes the
+// row block s of each 6x6 block: A (rows/cols of spin s, Hermitian 3x3) times the own part plus B (s = 0) / B^H (s = 1)
+// times the partner's part.  The two 6x6 blocks are a run-time loop (code size).
+__device__ __forceinline__ void clov_half(const float *__restrict__ Cs, const Ctx &cx_, const cf *x, cf *y) {
+  cf xm[3], xo[3], xmn[3], xon[3], ylo[3], yhi[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    xm[c] = x[c]; xmn[c] = x[3 + c];
+    xo[c] = cf(__shfl_xor_sync(0xffffffffu, x[c].re, 16), __shfl_xor_sync(0xffffffffu, x[c].im, 16));
+    xon[c] = cf(__shfl_xor_sync(0xffffffffu, x[3 + c].re, 16), __shfl_xor_sync(0xffffffffu, x[3 + c].im, 16));
+    ylo[c] = cf(0.f, 0.f); yhi[c] = cf(0.f, 0.f);
+  }
+  const int s = cx_.s;
+  const float cj = -cx_.sg;          // +1 for s = 0 (entries used as stored), -1 for s = 1 (conjugated)
+#pragma unroll 1
   for (int b = 0; b < 2; b++) {
+    const float *Cd = Cs + ((6 * b + 3 * s) << 5), *Ct = Cs + ((12 + 30 * b) << 5);
+    cf yo[3];
 #pragma unroll
-    for (int i = 0; i < 6; i++) y[6 * b + i] = __ldg(Cs + ((6 * b + i) << 5)) * x[6 * b + i];
-    int m = 0;
+    for (int i = 0; i < 3; i++) yo[i] = __ldg(Cd + (i << 5)) * xm[i];
 #pragma unroll
-    for (int i = 0; i < 6; i++)
+    for (int i = 0; i < 3; i++)
 #pragma unroll
-      for (int j = i + 1; j < 6; j++, m++) {
-        cf cij(__ldg(Cs + ((12 + 2 * (15 * b + m)) << 5)), __ldg(Cs + ((12 + 2 * (15 * b + m) + 1) << 5)));
-        fma_(y[6 * b + i], cij, x[6 * b + j]);
-        fmac_(y[6 * b + j], cij, x[6 * b + i]);
+      for (int j = i + 1; j < 3; j++) {
+        const int m = s ? tri(3 + i, 3 + j) : tri(i, j);
+        const cf a(__ldg(Ct + ((2 * m) << 5)), __ldg(Ct + ((2 * m + 1) << 5)));
+        fma_(yo[i], a, xm[j]);
+        fmac_(yo[j], a, xm[i]);
       }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int m = s ? tri(j, 3 + i) : tri(i, 3 + j);
+        const cf a(__ldg(Ct + ((2 * m) << 5)), cj * __ldg(Ct + ((2 * m + 1) << 5)));
+        fma_(yo[i], a, xo[j]);
+      }
+#pragma unroll
+    for (int c = 0; c < 3; c++) { ylo[c] = yhi[c]; yhi[c] = yo[c]; xm[c] = xmn[c]; xo[c] = xon[c]; }
   }
+#pragma unroll
+  for (int c = 0; c < 3; c++) { y[c] = ylo[c]; y[3 + c] = yhi[c]; }
 }
+
+__device__ __forceinline__ void load_own(const cf *v, long base, const Ctx &cx_, cf *out) {
+#pragma unroll
+  for (int c = 0; c < 3; c++) { out[c] = v[base + ((long)(cx_.up + c) << 5)]; out[3 + c] = v[base + ((long)(cx_.loA + c) << 5)]; }
+}
+
+struct SiteRef {       // everything that identifies one of the thread pair's two sites
+  int l; long s, v; const float *C; unsigned f, in, nf, nb;
+};
 
 // first_zero: x == 0 on the whole lattice on entry (first colour of a zero-guess call): r = eta, x = e.
-template <int BS>
-__global__ void __launch_bounds__(BS / 2, 2)
-k_sap_fine(FineOp<float> op, cf *__restrict__ x, const cf *__restrict__ eta, const int *__restrict__ blocklist,
-           int biter, int first_zero) {
+__global__ void __launch_bounds__(BS, 2)
+k_sap_fine(FineOp<float> op, cf *x, const cf *__restrict__ eta, const int *__restrict__ blocklist, int biter, int first_zero) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SapShared<BS> &sm = *reinterpret_cast<SapShared<BS> *>(smem_raw);
-  const int j = threadIdx.x, lane = j & 31, w = j >> 5;
-  const int H = BS / 2;
-  const int lE = j, lO = H + j;
+  Shared &sm = *reinterpret_cast<Shared *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  Ctx cx_;
+  cx_.s = lane >> 4; cx_.sg = cx_.s ? 1.f : -1.f;
+  cx_.up = 3 * cx_.s; cx_.loA = 6 + 3 * cx_.s; cx_.loB = 6 + 3 * (1 - cx_.s);
   const long base = (long)blocklist[blockIdx.x] * BS;
-  const long sE = base + lE, sO = base + lO;
   const long V = op.V;
-  // tiled global offsets (32-site tiles, component-major inside a tile)
-  const long tlE = sE >> 5, tlO = sO >> 5;
-  const long vE = tlE * (12L << 5) + lane, vO = tlO * (12L << 5) + lane;
-  const long cE = tlE * (72L << 5), cO = tlO * (72L << 5);
 
-  // links of the block -> shared memory (coalesced 256 B rows)
+  // links of the block -> shared memory: thread tid copies site tid (coalesced 256 B rows)
   {
     const float2 *D2 = reinterpret_cast<const float2 *>(op.D);
-    const long uE = tlE * (36L << 5) + lane, uO = tlO * (36L << 5) + lane;
+    const long st = base + tid;
+    const long u = (st >> 5) * (36L << 5) + (st & 31);
 #pragma unroll 4
-    for (int k = 0; k < 36; k++) {
-      sm.U[k][lE] = __ldg(D2 + uE + ((long)k << 5));
-      sm.U[k][lO] = __ldg(D2 + uO + ((long)k << 5));
-    }
+    for (int k = 0; k < 36; k++) sm.U[k][tid] = __ldg(D2 + u + ((long)k << 5));
   }
-  // in-block neighbour indices (blocks are contiguous site ranges in the native order)
-  const unsigned fE = op.blkflag[sE], fO = op.blkflag[sO];
-  unsigned nfE = 0, nbE = 0, nfO = 0, nbO = 0;
-#pragma unroll
-  for (int d = 0; d < 4; d++) {
-    nfE |= (unsigned)((__ldg(op.nb + (long)d * V + sE) - base) & 0xFF) << (8 * d);
-    nbE |= (unsigned)((__ldg(op.nb + (long)(4 + d) * V + sE) - base) & 0xFF) << (8 * d);
-    nfO |= (unsigned)((__ldg(op.nb + (long)d * V + sO) - base) & 0xFF) << (8 * d);
-    nbO |= (unsigned)((__ldg(op.nb + (long)(4 + d) * V + sO) - base) & 0xFF) << (8 * d);
-  }
-  const unsigned inE = (~fE) & 0xFFu, inO = (~fO) & 0xFFu;
-
-  cf rE[12], rO[12];
-#pragma unroll
-  for (int c = 0; c < 12; c++) { rE[c] = eta[vE + ((long)c << 5)]; rO[c] = eta[vO + ((long)c << 5)]; }
-  if (!first_zero) {
-    // r = eta - D x on the block: clover + in-block hops (shared memory) + couplings to neighbouring blocks (global)
-    cf xE[12], xO[12], y[12];
-#pragma unroll
-    for (int c = 0; c < 12; c++) { xE[c] = x[vE + ((long)c << 5)]; xO[c] = x[vO + ((long)c << 5)]; }
-    put<BS>(sm, lE, xE); put<BS>(sm, lO, xO);
-    clov(op.C, cE, lane, xE, y);
-#pragma unroll
-    for (int c = 0; c < 12; c++) rE[c] -= y[c];
-    clov(op.C, cO, lane, xO, y);
-#pragma unroll
-    for (int c = 0; c < 12; c++) rO[c] -= y[c];
-    // cross-block hops: hop_pair subtracts from its accumulator, so accumulate -N x into y and add
-#pragma unroll
-    for (int c = 0; c < 12; c++) y[c] = cf(0.f, 0.f);
-    if (fE) { hop_pair<0>(op, sE, fE, x, y); hop_pair<1>(op, sE, fE, x, y); hop_pair<2>(op, sE, fE, x, y); hop_pair<3>(op, sE, fE, x, y); }
-#pragma unroll
-    for (int c = 0; c < 12; c++) { rE[c] -= y[c]; y[c] = cf(0.f, 0.f); }
-    if (fO) { hop_pair<0>(op, sO, fO, x, y); hop_pair<1>(op, sO, fO, x, y); hop_pair<2>(op, sO, fO, x, y); hop_pair<3>(op, sO, fO, x, y); }
-#pragma unroll
-    for (int c = 0; c < 12; c++) { rO[c] -= y[c]; y[c] = cf(0.f, 0.f); }
-    __syncthreads();
-    sm_hops<BS>(sm, lE, inE, nfE, nbE, y);
-#pragma unroll
-    for (int c = 0; c < 12; c++) { rE[c] -= y[c]; y[c] = cf(0.f, 0.f); }
-    sm_hops<BS>(sm, lO, inO, nfO, nbO, y);
-#pragma unroll
-    for (int c = 0; c < 12; c++) rO[c] -= y[c];
-  }
-  __syncthreads();
-
-  // e_o = Doo^-1 r_o ; t_e = r_e - N_eo e_o        (hop accumulators hold N v with the operator's sign: D = C + N)
-  cf tE[12], eE[12];
+  // the pair's even site E and odd site O: block-local index, global index, offsets, in-block neighbour indices
+  SiteRef E, O;
+  E.l = 16 * w + (lane & 15); O.l = BS / 2 + E.l;
   {
-    cf eO[12];
-    clov(op.Cinv, cO, lane, rO, eO);
-    put<BS>(sm, lO, eO);
-  }
-  __syncthreads();
-  {
-    cf y[12];
+    SiteRef *sr[2] = {&E, &O};
 #pragma unroll
-    for (int c = 0; c < 12; c++) y[c] = cf(0.f, 0.f);
-    sm_hops<BS>(sm, lE, inE, nfE, nbE, y);
+    for (int p = 0; p < 2; p++) {
+      SiteRef &R = *sr[p];
+      R.s = base + R.l;
+      R.v = (R.s >> 5) * (12L << 5) + (R.s & 31);
+      R.C = op.C + (R.s >> 5) * (72L << 5) + (R.s & 31);
+      R.f = op.blkflag[R.s]; R.in = (~R.f) & 0xFFu; R.nf = 0; R.nb = 0;
 #pragma unroll
-    for (int c = 0; c < 12; c++) { tE[c] = rE[c] - y[c]; eE[c] = cf(0.f, 0.f); }
-  }
-  // minimal residual on S = C_ee - N_eo Coo^-1 N_oe
-  for (int it = 0; it < biter; it++) {
-    put<BS>(sm, lE, tE);
-    __syncthreads();
-    {
-      cf a[12], a2[12];
-#pragma unroll
-      for (int c = 0; c < 12; c++) a[c] = cf(0.f, 0.f);
-      sm_hops<BS>(sm, lO, inO, nfO, nbO, a);          // a_o = N_oe t_e
-      clov(op.Cinv, cO, lane, a, a2);
-#pragma unroll
-      for (int c = 0; c < 12; c++) a2[c] = -a2[c];      // a2_o = -Coo^-1 a_o
-      put<BS>(sm, lO, a2);
-    }
-    __syncthreads();
-    cf Dr[12];
-    clov(op.C, cE, lane, tE, Dr);
-    {
-      cf y[12];
-#pragma unroll
-      for (int c = 0; c < 12; c++) y[c] = cf(0.f, 0.f);
-      sm_hops<BS>(sm, lE, inE, nfE, nbE, y);           // N_eo a2_o
-#pragma unroll
-      for (int c = 0; c < 12; c++) Dr[c] += y[c];
-    }
-    // alpha = <Dr,t>/<Dr,Dr> over the even sites of the block
-    float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-#pragma unroll
-    for (int c = 0; c < 12; c++) {
-      p0 += Dr[c].re * tE[c].re + Dr[c].im * tE[c].im;
-      p1 += Dr[c].re * tE[c].im - Dr[c].im * tE[c].re;
-      p2 += Dr[c].re * Dr[c].re + Dr[c].im * Dr[c].im;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o);
-    }
-    float (*red)[4] = sm.red[it & 1];
-    if (lane == 0) { red[w][0] = p0; red[w][1] = p1; red[w][2] = p2; }
-    __syncthreads();
-    p0 = p1 = p2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < BS / 64; k++) { p0 += red[k][0]; p1 += red[k][1]; p2 += red[k][2]; }
-    cf alpha(0.f, 0.f);
-    if (p2 > 1e-30f) alpha = cf(p0 / p2, p1 / p2);
-#pragma unroll
-    for (int c = 0; c < 12; c++) { fma_(eE[c], alpha, tE[c]); fms_(tE[c], alpha, Dr[c]); }
-  }
-  // back substitution: e_o = Coo^-1 (r_o - N_oe e_e) ; x += e
-  put<BS>(sm, lE, eE);
-  __syncthreads();
-  {
-    cf y[12], eO[12];
-#pragma unroll
-    for (int c = 0; c < 12; c++) y[c] = cf(0.f, 0.f);
-    sm_hops<BS>(sm, lO, inO, nfO, nbO, y);
-#pragma unroll
-    for (int c = 0; c < 12; c++) y[c] = rO[c] - y[c];
-    clov(op.Cinv, cO, lane, y, eO);
-    if (first_zero) {
-#pragma unroll
-      for (int c = 0; c < 12; c++) { x[vE + ((long)c << 5)] = eE[c]; x[vO + ((long)c << 5)] = eO[c]; }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 12; c++) {
-        cf a = x[vE + ((long)c << 5)], b = x[vO + ((long)c << 5)];
-        x[vE + ((long)c << 5)] = a + eE[c]; x[vO + ((long)c << 5)] = b + eO[c];
+      for (int d = 0; d < 4; d++) {
+        R.nf |= (unsigned)((__ldg(op.nb + (long)d * V + R.s) - base) & 0xFF) << (8 * d);
+        R.nb |= (unsigned)((__ldg(op.nb + (long)(4 + d) * V + R.s) - base) & 0xFF) << (8 * d);
       }
     }
   }
+  const float *CinvO = op.Cinv + (O.s >> 5) * (72L << 5) + (O.s & 31);
+
+  cf rE[6], rO[6];
+  load_own(eta, E.v, cx_, rE); load_own(eta, O.v, cx_, rO);
+  if (!first_zero) {
+    // r = eta - D x on the block: clover + couplings to neighbouring blocks (global) + in-block hops (shared memory);
+    // the two sites of the pair run through ONE copy of the code (register rotation at the loop end)
+    SiteRef A = E, B = O;
+    cf ra[6], rb[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) { ra[c] = rE[c]; rb[c] = rO[c]; }
+#pragma unroll 1
+    for (int p = 0; p < 2; p++) {
+      cf xa[6], y[6];
+      load_own(x, A.v, cx_, xa);
+      put(sm, cx_, A.l, xa);
+      clov_half(A.C, cx_, xa, y);
+#pragma unroll
+      for (int c = 0; c < 6; c++) ra[c] -= y[c];
+      gl_hops(op, cx_, A.s, A.f, x, y);
+#pragma unroll
+      for (int c = 0; c < 6; c++) { ra[c] -= y[c]; const cf t = ra[c]; ra[c] = rb[c]; rb[c] = t; }
+      const SiteRef T = A; A = B; B = T;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int p = 0; p < 2; p++) {
+      cf y[6];
+      sm_hops(sm, cx_, A.l, A.in, A.nf, A.nb, y);
+#pragma unroll
+      for (int c = 0; c < 6; c++) { ra[c] -= y[c]; const cf t = ra[c]; ra[c] = rb[c]; rb[c] = t; }
+      const SiteRef T = A; A = B; B = T;
+    }
+#pragma unroll
+    for (int c = 0; c < 6; c++) { rE[c] = ra[c]; rO[c] = rb[c]; }
+    __syncthreads();
+  }
+
+  // block solve.  k = 0: e_o = Coo^-1 r_o, t_e = r_e - N_eo e_o.   k = 1..biter: one MR step on the Schur complement
+  // S = C_ee - N_eo Coo^-1 N_oe.   k = biter+1: back substitution e_o = Coo^-1 (r_o - N_oe e_e), x += e.
+  cf tE[6], eE[6];
+#pragma unroll
+  for (int c = 0; c < 6; c++) { tE[c] = cf(0.f, 0.f); eE[c] = cf(0.f, 0.f); }
+#pragma unroll 1
+  for (int k = 0; k <= biter + 1; k++) {
+    cf wv[6], z[6];
+    if (k > 0) sm_hops(sm, cx_, O.l, O.in, O.nf, O.nb, wv);          // N_oe (t_e or e_e)
+    if (k == 0) {
+#pragma unroll
+      for (int c = 0; c < 6; c++) wv[c] = rO[c];
+    } else if (k == biter + 1) {
+#pragma unroll
+      for (int c = 0; c < 6; c++) wv[c] = rO[c] - wv[c];
+    }
+    clov_half(CinvO, cx_, wv, z);
+    if (k == biter + 1) {
+      // x += e
+      if (!first_zero) {
+        cf a[6], b[6];
+        load_own(x, E.v, cx_, a); load_own(x, O.v, cx_, b);
+#pragma unroll
+        for (int c = 0; c < 6; c++) { eE[c] += a[c]; z[c] += b[c]; }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        x[E.v + ((long)(cx_.up + c) << 5)] = eE[c]; x[E.v + ((long)(cx_.loA + c) << 5)] = eE[3 + c];
+        x[O.v + ((long)(cx_.up + c) << 5)] = z[c]; x[O.v + ((long)(cx_.loA + c) << 5)] = z[3 + c];
+      }
+      break;
+    }
+    if (k > 0) {
+#pragma unroll
+      for (int c = 0; c < 6; c++) z[c] = -z[c];                        // a2_o = -Coo^-1 N_oe t_e
+    }
+    put(sm, cx_, O.l, z);
+    __syncthreads();
+    cf y[6];
+    sm_hops(sm, cx_, E.l, E.in, E.nf, E.nb, y);                      // N_eo (e_o or a2_o)
+    if (k == 0) {
+#pragma unroll
+      for (int c = 0; c < 6; c++) tE[c] = rE[c] - y[c];
+    } else {
+      cf Dr[6];
+      clov_half(E.C, cx_, tE, Dr);
+#pragma unroll
+      for (int c = 0; c < 6; c++) Dr[c] += y[c];
+      // alpha = <Dr,t>/<Dr,Dr> over the even sites of the block (local_minres, linsolve_generic.c:1013-1022)
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        p0 += Dr[c].re * tE[c].re + Dr[c].im * tE[c].im;
+        p1 += Dr[c].re * tE[c].im - Dr[c].im * tE[c].re;
+        p2 += Dr[c].re * Dr[c].re + Dr[c].im * Dr[c].im;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+      }
+      float (*red)[4] = sm.red[k & 1];
+      if (lane == 0) { red[w][0] = p0; red[w][1] = p1; red[w][2] = p2; }
+      __syncthreads();
+      p0 = p1 = p2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < BS / 32; i++) { p0 += red[i][0]; p1 += red[i][1]; p2 += red[i][2]; }
+      cf alpha(0.f, 0.f);
+      if (p2 > 1e-30f) alpha = cf(p0 / p2, p1 / p2);
+#pragma unroll
+      for (int c = 0; c < 6; c++) { fma_(eE[c], alpha, tE[c]); fms_(tE[c], alpha, Dr[c]); }
+    }
+    put(sm, cx_, E.l, (k < biter) ? tE : eE);
+    __syncthreads();
+  }
 }
+
+}  // namespace sap
 
 // fine-level SAP with the fused block kernel; same iteration as the generic path of mg_smoother
 bool sap_fine_fast_available(const Solver &s) {
@@ -267,9 +404,9 @@ void sap_fine_fast(Solver &s, cf *x, const cf *eta, int iters, bool zero_guess) 
   const Geometry &g = L.geo;
   const int biter = s.p.block_iter[0];
   static bool attr_set = false;
-  const int smem = (int)sizeof(SapShared<256>);
+  const int smem = (int)sizeof(sap::Shared);
   if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_sap_fine<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(sap::k_sap_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   if (zero_guess) vzero(x, g.vlen());
@@ -279,7 +416,7 @@ void sap_fine_fast(Solver &s, cf *x, const cf *eta, int iters, bool zero_guess) 
       if (nblk == 0) continue;
       const int first = (zero_guess && cyc == 0 && col == 0) ? 1 : 0;
       if (!first) halo_exchange<cf>(g, x, 12, g.sh);   // block residuals read x of neighbouring blocks on other ranks
-      k_sap_fine<256><<<nblk, 128, smem, g_stream>>>(L.opf, x, eta, g.d_blocklist[col], biter, first);
+      sap::k_sap_fine<<<nblk, sap::BS, smem, g_stream>>>(L.opf, x, eta, g.d_blocklist[col], biter, first);
       g_launch_count++;
 #ifdef DDA_DEBUG_SYNC
       CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());

@@ -9,7 +9,13 @@ long tr_scratch_doubles(const Transfer &t) { return (long)t.nagg * 2 * t.nv * 2 
 
 // phi_c(a)[ch*nv + k] = sum over the sites of aggregate a and the dofs of chirality ch of conj(P_k) * phi
 // reference: restrict_PRECISION, interpolation_generic.c:169-207
+bool tr_restrict_fast(const Transfer &t, cf *out, long site_stride, long offset, const cf *phi);
+int g_transfer_fast = 1;
+
 void tr_restrict(const Transfer &t, cf *out, long site_stride, long offset, const cf *phi, double *scratch) {
+#ifndef DDA_HOST_EMU
+  if (g_transfer_fast && tr_restrict_fast(t, out, site_stride, offset, phi)) return;
+#endif
   const int nv = t.nv, h = t.nc / 2, as = t.as;
   const long nseg = (long)t.nagg * 2 * nv, seglen = (long)as * h;
   const Transfer tt = t;

@@ -31,5 +31,6 @@ void tr_gram_schmidt_aggregates(const Transfer &t, cf *const *vecs, double *scra
 // v = chirality part `ch` of src (other chirality zeroed)
 void tr_chirality_part(const Transfer &t, cf *v, const cf *src, int ch);
 long tr_scratch_doubles(const Transfer &t);
+extern int g_transfer_fast;   // 1: hand-tuned kernels where available (follows Solver::use_fast)
 
 }  // namespace dda
