@@ -32,7 +32,8 @@ void coarse_apply(const CoarseOp &op, cf *out, const cf *in, SiteSel sel, int ho
 // Sinv = S^{-1} on the odd sites of the coarsest level (dense inversion in double, no pivoting; the reference
 // factorises LU without pivoting, coarse_oddeven_generic.c:24-73)
 void coarse_invert_odd_self(CoarseOp &op);
-// optimised full-lattice apply (sm_100a only; coarse_kernel.cu)
-void coarse_apply_fast(const CoarseOp &op, cf *out, const cf *in);
+// optimised full-lattice apply (sm_100a only; coarse_kernel.cu); Z: scratch of 4*n complex per site.  Returns false
+// when the shape is not supported (caller falls back to coarse_apply).
+bool coarse_apply_fast(const CoarseOp &op, cf *out, const cf *in, cf *Z);
 
 }  // namespace dda

@@ -28,13 +28,15 @@ void lv_apply(Level &L, cf *out, const cf *in, SiteSel sel, int hop, int dir, in
   else coarse_apply(L.cop, out, in, sel, hop, dir, self, outmode, eta, in_self);
 }
 
-void coarse_apply_fast(const CoarseOp &op, cf *out, const cf *in, cf *scratch);
 
 void mg_apply_op(Solver &s, int depth, cf *out, const cf *in) {
   Level &L = s.lev[depth];
   ProfScope ps(s, &s.t_op[depth]);
   if (depth == 0) { solver_apply_dw<float>(s, out, in); return; }
   lv_halo(L, in);
+#ifndef DDA_HOST_EMU
+  if (s.use_fast && coarse_apply_fast(L.cop, out, in, L.copZ)) return;
+#endif
   lv_apply(L, out, in, sel_all(L.geo.V), HOP_ALL, 0, SELF_C, OUT_SET);
 }
 

@@ -51,6 +51,7 @@ void mg_alloc(Solver &s) {
       c.F = dev_alloc<cf>((g.V + g.Vg) * 4 * nn); c.S = dev_alloc<cf>(g.V * nn);   // hops of the ghost sites too
       c.Sinv = (L.last && p.odd_even) ? dev_alloc<cf>((g.V - c.n_even) * nn) : nullptr;
       c.nb = g.d_nb; c.blkflag = g.d_blkflag; c.aggflag = g.d_aggflag;
+      L.copZ = dev_alloc<cf>(g.V * 4 * c.n);
     }
   }
   for (int d = 0; d < s.nlev; d++) {
@@ -99,7 +100,7 @@ void mg_free(Solver &s) {
     for (int i = 0; i < NWORK; i++) { dev_free(L.w[i]); L.w[i] = nullptr; }
     L.kc.release();
     if (d > 0) {
-      dev_free(L.cop.F); dev_free(L.cop.S); dev_free(L.cop.Sinv);
+      dev_free(L.cop.F); dev_free(L.cop.S); dev_free(L.cop.Sinv); dev_free(L.copZ); L.copZ = nullptr;
       L.cop.F = L.cop.S = L.cop.Sinv = nullptr;
       L.geo.destroy();
     } else {

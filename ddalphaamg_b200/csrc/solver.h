@@ -23,6 +23,7 @@ struct Level {
   FineOp<double> opd; FineOp<float> opf;
   // ---- coarse levels (depth >= 1)
   CoarseOp cop;
+  cf *copZ = nullptr;                    // scratch of the scatter-form coarse apply (4 n complex per site)
   // ---- transfer to depth+1
   std::vector<cf *> tv;   // test vectors
   std::vector<cf *> P;    // interpolation vectors = aggregate/chirality-orthonormalised test vectors
