@@ -47,15 +47,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// Register tiling: thread t of the 128 owns the component PAIR p = t % (n/2) of group g = t / (n/2)  (G groups, G | n/2
+// chosen by the host, threads beyond G*n/2 idle).  Forward product: rows 2p, 2p+1 times the group's chunk of n/G
+// columns; daggered product: columns 2p, 2p+1 times the group's chunk of rows.  Both walk the column-major block with
+// 16-byte shared-memory loads (two complex per load); the daggered walk is rotated by p row pairs, which makes the
+// stride-n column accesses bank-conflict free.  ~4.75 instructions per complex multiply-add (4 are the FFMAs).
+// Partial sums stay in registers over the 5 blocks of a site and are combined once per site.
 template <int STAGES>
 __global__ void __launch_bounds__(128)
-k_coarse_full(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *__restrict__ Z, int nsites) {
+k_coarse_full(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *__restrict__ Z, int nsites, int G) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int n = op.n, nn = n * n, nh = n / 2;
+  const int n = op.n, nn = n * n, nh = n / 2, P = n / 2;
+  const int ch = n / G;                                         // even chunk of columns (forward) / rows (daggered)
   cf *Ms = reinterpret_cast<cf *>(smem_raw);                    // [STAGES][n*n]
   cf *vec = Ms + (size_t)STAGES * nn;                           // [6][n]: v(x), v(x+mu) x4, gamma5 v(x)
-  uint64_t *full = reinterpret_cast<uint64_t *>(vec + 6 * n);   // [STAGES]
+  cf *part = vec + 6 * n;                                       // [5][G][n] partial sums (forward, 4 x daggered)
+  uint64_t *full = reinterpret_cast<uint64_t *>(part + 5 * G * n);   // [STAGES]
   const int tid = threadIdx.x;
+  const int grp = tid / P, p = tid - grp * P;
+  const bool active = grp < G;
   const uint32_t bytes = (uint32_t)(nn * sizeof(cf));
   const int my_sites = (nsites - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total = 5 * my_sites;
@@ -76,47 +86,97 @@ k_coarse_full(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
   };
   if (tid == 0) for (int j = 0; j < STAGES && j < total; j++) issue(j);
 
+  // the input vectors of a site (5 n complex: phi(x), phi(x+mu)) are fetched one site ahead into registers, so that the
+  // dependent index -> vector loads are in flight while the previous site's blocks are processed
+  cf pre[3];
+  auto prefetch = [&](int k) {
+    const long x = (long)blockIdx.x + (long)k * gridDim.x;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const int q = tid + 128 * i;
+      if (q < 5 * n) {
+        const int vsel = q / n, c = q - vsel * n;
+        const long src = (vsel == 0) ? x : (long)op.nb[(long)(vsel - 1) * op.V + x];
+        pre[i] = in[src * n + c];
+      }
+    }
+  };
+  if (my_sites > 0) prefetch(0);
+
   for (int k = 0; k < my_sites; k++) {
     const long x = (long)blockIdx.x + (long)k * gridDim.x;
-    if (tid < n) {
-      const cf v = in[x * n + tid];
-      vec[tid] = v;
-      vec[5 * n + tid] = (tid < nh) ? v : -v;
 #pragma unroll
-      for (int mu = 0; mu < 4; mu++) vec[(1 + mu) * n + tid] = in[(long)op.nb[(long)mu * op.V + x] * n + tid];
+    for (int i = 0; i < 3; i++) {
+      const int q = tid + 128 * i;
+      if (q < 5 * n) {
+        vec[q] = pre[i];
+        if (q < n) vec[5 * n + q] = (q < nh) ? pre[i] : -pre[i];
+      }
     }
     __syncthreads();
-    cf acc(0.f, 0.f);
+    if (k + 1 < my_sites) prefetch(k + 1);
+    float f0r = 0.f, f0i = 0.f, f1r = 0.f, f1i = 0.f;             // forward rows 2p, 2p+1
+    float zr[4][2], zi[4][2];                                     // daggered columns 2p, 2p+1 per direction
+#pragma unroll
+    for (int mu = 0; mu < 4; mu++) { zr[mu][0] = zr[mu][1] = zi[mu][0] = zi[mu][1] = 0.f; }
+#pragma unroll
     for (int m = 0; m < 5; m++) {
       const int j = 5 * k + m, st = j % STAGES;
       mbar_wait(&full[st], (uint32_t)((j / STAGES) & 1));
       const cf *M = Ms + (size_t)st * nn;
-      if (tid < n) {                      // forward: row tid of M times v
-        const cf *v = vec + m * n;
-        cf a0(0.f, 0.f), a1(0.f, 0.f);
-        int c = 0;
-        for (; c + 1 < n; c += 2) { fma_(a0, M[c * n + tid], v[c]); fma_(a1, M[(c + 1) * n + tid], v[c + 1]); }
-        if (c < n) fma_(a0, M[c * n + tid], v[c]);
-        acc += a0 + a1;
-      } else if (tid < 2 * n && m > 0) {  // daggered: column (tid - n) of M, conjugated, times gamma5 v(x)
-        const int col = tid - n;
-        const cf *Mc = M + col * n, *w = vec + 5 * n;
-        cf a0(0.f, 0.f), a1(0.f, 0.f);
-        int rr = col;                     // rotated start: bank-conflict free column walk
-        int r = 0;
-        for (; r + 1 < n; r += 2) {
-          fmac_(a0, Mc[rr], w[rr]); rr++; if (rr == n) rr = 0;
-          fmac_(a1, Mc[rr], w[rr]); rr++; if (rr == n) rr = 0;
+      if (active) {
+        {                                 // forward
+          const float4 *v4 = reinterpret_cast<const float4 *>(vec + m * n + grp * ch);
+          const cf *Mb = M + (size_t)(grp * ch) * n + 2 * p;
+#pragma unroll 2
+          for (int cc = 0; cc < ch; cc += 2) {
+            const float4 v = v4[cc >> 1];
+            const float4 m0 = *reinterpret_cast<const float4 *>(Mb + (size_t)cc * n);
+            const float4 m1 = *reinterpret_cast<const float4 *>(Mb + (size_t)(cc + 1) * n);
+            f0r += m0.x * v.x - m0.y * v.y; f0i += m0.x * v.y + m0.y * v.x;
+            f1r += m0.z * v.x - m0.w * v.y; f1i += m0.z * v.y + m0.w * v.x;
+            f0r += m1.x * v.z - m1.y * v.w; f0i += m1.x * v.w + m1.y * v.z;
+            f1r += m1.z * v.z - m1.w * v.w; f1i += m1.z * v.w + m1.w * v.z;
+          }
         }
-        if (r < n) fmac_(a0, Mc[rr], w[rr]);
-        cf z = a0 + a1;
-        if (col >= nh) z = -z;
-        Z[(x * 4 + (m - 1)) * n + col] = z;
+        if (m > 0) {                      // daggered: conj(M[r][c]) w[r]
+          const cf *w = vec + 5 * n;
+          const cf *M0 = M + (size_t)(2 * p) * n, *M1 = M0 + n;
+          float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;
+          int ip = grp * (ch >> 1) + p; if (ip >= P) ip -= P;    // rotated row pair
+#pragma unroll 2
+          for (int i = 0; i < (ch >> 1); i++) {
+            const float4 wv = *reinterpret_cast<const float4 *>(w + 2 * ip);
+            const float4 m0 = *reinterpret_cast<const float4 *>(M0 + 2 * ip);
+            const float4 m1 = *reinterpret_cast<const float4 *>(M1 + 2 * ip);
+            a0r += m0.x * wv.x + m0.y * wv.y; a0i += m0.x * wv.y - m0.y * wv.x;
+            a0r += m0.z * wv.z + m0.w * wv.w; a0i += m0.z * wv.w - m0.w * wv.z;
+            a1r += m1.x * wv.x + m1.y * wv.y; a1i += m1.x * wv.y - m1.y * wv.x;
+            a1r += m1.z * wv.z + m1.w * wv.w; a1i += m1.z * wv.w - m1.w * wv.z;
+            ip++; if (ip == P) ip = 0;
+          }
+          zr[m - 1][0] = a0r; zi[m - 1][0] = a0i; zr[m - 1][1] = a1r; zi[m - 1][1] = a1i;
+        }
       }
       __syncthreads();
       if (tid == 0 && j + STAGES < total) issue(j + STAGES);
     }
-    if (tid < n) out[x * n + tid] = acc;
+    // combine the G partial sums
+    if (active) {
+      float4 *pf = reinterpret_cast<float4 *>(part + grp * n + 2 * p);
+      *pf = make_float4(f0r, f0i, f1r, f1i);
+#pragma unroll
+      for (int mu = 0; mu < 4; mu++)
+        *reinterpret_cast<float4 *>(part + ((1 + mu) * G + grp) * n + 2 * p) = make_float4(zr[mu][0], zi[mu][0], zr[mu][1], zi[mu][1]);
+    }
+    __syncthreads();
+    for (int q = tid; q < 5 * n; q += 128) {
+      const int sel = q / n, c = q - sel * n;
+      cf a = part[(sel * G) * n + c];
+      for (int g2 = 1; g2 < G; g2++) a += part[(sel * G + g2) * n + c];
+      if (sel == 0) out[x * n + c] = a;
+      else Z[(x * 4 + (sel - 1)) * n + c] = (c < nh) ? a : -a;
+    }
   }
 }
 
@@ -144,24 +204,33 @@ __global__ void k_coarse_combine(CoarseOp op, cf *__restrict__ out, const cf *__
   out[i] = acc;
 }
 
+int g_coarse_stages = 0;   // 0: default; 3 / 4: force the depth of the TMA ring (tuning knob, env DDA_COARSE_STAGES)
+
 bool coarse_apply_fast(const CoarseOp &op, cf *out, const cf *in, cf *Z) {
+  static bool env_read = false;
+  if (!env_read) { const char *e = getenv("DDA_COARSE_STAGES"); if (e) g_coarse_stages = atoi(e); env_read = true; }
   const int n = op.n;
-  if (n > 64 || (n & 1) || !Z || op.V <= 0) return false;
+  if (n > 64 || n < 8 || (n & 3) || !Z || op.V <= 0) return false;
   const size_t nn = (size_t)n * n;
   int dev = 0; cudaGetDevice(&dev);
   static int sms = 0;
   if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int stages = n <= 48 ? 4 : 3;
-  const size_t smem = stages * nn * sizeof(cf) + 6 * n * sizeof(cf) + 8 * sizeof(uint64_t);
-  static size_t attr4 = 0, attr3 = 0;
+  const int stages = (g_coarse_stages >= 2 && g_coarse_stages <= 4) ? g_coarse_stages : 2;   // measured on B200: 2 stages x 7 CTAs/SM beats deeper rings
+  int G = 128 / (n / 2);
+  while (G > 1 && n % (2 * G) != 0) G--;          // even chunk n / G
+  if (n % (2 * G) != 0) return false;
+  const size_t smem = stages * nn * sizeof(cf) + (6 + 5 * G) * n * sizeof(cf) + 8 * sizeof(uint64_t);
+  static size_t attr4 = 0, attr3 = 0, attr2 = 0;
+  if (stages == 2 && smem > attr2) { CUDA_CHECK(cudaFuncSetAttribute(k_coarse_full<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr2 = smem; }
   if (stages == 4 && smem > attr4) { CUDA_CHECK(cudaFuncSetAttribute(k_coarse_full<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr4 = smem; }
   if (stages == 3 && smem > attr3) { CUDA_CHECK(cudaFuncSetAttribute(k_coarse_full<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr3 = smem; }
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) return false;
-  if (per_sm > 8) per_sm = 8;
+  if (per_sm > 12) per_sm = 12;
   long grid = std::min<long>(op.V, (long)sms * per_sm);
-  if (stages == 4) k_coarse_full<4><<<(unsigned)grid, 128, smem, g_stream>>>(op, out, in, Z, (int)op.V);
-  else k_coarse_full<3><<<(unsigned)grid, 128, smem, g_stream>>>(op, out, in, Z, (int)op.V);
+  if (stages == 2) k_coarse_full<2><<<(unsigned)grid, 128, smem, g_stream>>>(op, out, in, Z, (int)op.V, G);
+  else if (stages == 4) k_coarse_full<4><<<(unsigned)grid, 128, smem, g_stream>>>(op, out, in, Z, (int)op.V, G);
+  else k_coarse_full<3><<<(unsigned)grid, 128, smem, g_stream>>>(op, out, in, Z, (int)op.V, G);
   g_launch_count++;
   const long total = op.V * n;
   k_coarse_combine<<<(unsigned)((total + 127) / 128), 128, 0, g_stream>>>(op, out, in, Z, total);
