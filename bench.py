@@ -41,6 +41,9 @@ WORKLOADS = {
     "48^3x96-L3": dict(lattice=[96, 48, 48, 48], levels=3, test_vectors=(20, 28), setup_iter=(3, 2), m0=-0.1,
                        coarse_block=[3, 2, 2, 2],
                        config="configs[3]: 48^3x96 synthetic gauge field, 3-level AMG"),
+    "64^3x128-L3": dict(lattice=[128, 64, 64, 64], levels=3, test_vectors=(20, 28), setup_iter=(3, 2), m0=-0.1,
+                        coarse_block=[2, 2, 2, 2],
+                        config="configs[4]: 64^3x128 synthetic gauge field, 3-level AMG (needs >= 4 GPUs; single RHS)"),
 }
 DEFAULT_WORKLOAD = "48^3x96-L3"
 CPU_SAMPLE = {2: [16, 8, 8, 8], 3: [16, 16, 16, 16]}
@@ -271,6 +274,12 @@ def run_native(args, w, name):
     bs = S.info(INFO.BLOCK_SITES, 0)
     sap_ms = S.bench_op(BENCH.SMOOTHER, 0, 5)
     add("sap_smoother_d0", sap_ms, 2 * nblk * (bs * (288 + 336) + 5 * bs * 96.0))
+    for d in range(1, nlev - 1):
+        # coarse-level SAP (2 iterations x 2 colours): per colour the block residual (operator on half the sites) and
+        # block_iter block-operator applications (self coupling + in-block hops ~ 3 blocks of n^2 per site)
+        Vd, nc = S.level_shape(d)
+        per_colour = (Vd / 2) * ((4 * nc * nc + nc * (nc + 1) // 2) + 4 * 3 * nc * nc) * 8.0
+        add("sap_smoother_d%d" % d, S.bench_op(BENCH.SMOOTHER, d, 3), 4 * per_colour)
 
     torch.cuda.profiler.stop()
 
