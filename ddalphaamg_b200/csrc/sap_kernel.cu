@@ -34,6 +34,7 @@ struct Shared {
   float2 U[36][BS];                 // links of the block's sites, [9*mu + 3*row + col][site]
   float2 Vb[12][BS];                // exchange buffer [component][site in block]
   float red[2][BS / 32][4];
+  float2 stash[6][BS];               // per-thread copy of r_o (needed only at the first and the last step of the block solve)
 };
 
 struct Ctx {                        // per-thread constants of the pair decomposition
@@ -72,9 +73,9 @@ __device__ __forceinline__ void half_hop(const cf *pu, const cf *pl, const cf *M
   }
 #pragma unroll
   for (int r = 0; r < 3; r++) {
-    cf a(0.f, 0.f);
+    cf a;
     if (S > 0) { a = M[3 * r] * h[0]; fma_(a, M[3 * r + 1], h[1]); fma_(a, M[3 * r + 2], h[2]); }
-    else { fmac_(a, M[r], h[0]); fmac_(a, M[3 + r], h[1]); fmac_(a, M[6 + r], h[2]); }
+    else { a = conj(M[r]) * h[0]; fmac_(a, M[3 + r], h[1]); fmac_(a, M[6 + r], h[2]); }
     g[r] = a;
   }
 #pragma unroll
@@ -317,19 +318,20 @@ k_sap_fine(FineOp<float> op, cf *x, const cf *__restrict__ eta, const int *__res
 
   // block solve.  k = 0: e_o = Coo^-1 r_o, t_e = r_e - N_eo e_o.   k = 1..biter: one MR step on the Schur complement
   // S = C_ee - N_eo Coo^-1 N_oe.   k = biter+1: back substitution e_o = Coo^-1 (r_o - N_oe e_e), x += e.
+  // Register budget (128): r_e lives on only as the initial value of t_e, r_o is parked in shared memory.
   cf tE[6], eE[6];
 #pragma unroll
-  for (int c = 0; c < 6; c++) { tE[c] = cf(0.f, 0.f); eE[c] = cf(0.f, 0.f); }
+  for (int c = 0; c < 6; c++) { tE[c] = rE[c]; eE[c] = cf(0.f, 0.f); sm.stash[c][tid] = make_float2(rO[c].re, rO[c].im); }
 #pragma unroll 1
   for (int k = 0; k <= biter + 1; k++) {
     cf wv[6], z[6];
     if (k > 0) sm_hops(sm, cx_, O.l, O.in, O.nf, O.nb, wv);          // N_oe (t_e or e_e)
     if (k == 0) {
 #pragma unroll
-      for (int c = 0; c < 6; c++) wv[c] = rO[c];
+      for (int c = 0; c < 6; c++) wv[c] = ld2(sm.stash[c][tid]);
     } else if (k == biter + 1) {
 #pragma unroll
-      for (int c = 0; c < 6; c++) wv[c] = rO[c] - wv[c];
+      for (int c = 0; c < 6; c++) wv[c] = ld2(sm.stash[c][tid]) - wv[c];
     }
     clov_half(CinvO, cx_, wv, z);
     if (k == biter + 1) {
@@ -357,7 +359,7 @@ k_sap_fine(FineOp<float> op, cf *x, const cf *__restrict__ eta, const int *__res
     sm_hops(sm, cx_, E.l, E.in, E.nf, E.nb, y);                      // N_eo (e_o or a2_o)
     if (k == 0) {
 #pragma unroll
-      for (int c = 0; c < 6; c++) tE[c] = rE[c] - y[c];
+      for (int c = 0; c < 6; c++) tE[c] -= y[c];
     } else {
       cf Dr[6];
       clov_half(E.C, cx_, tE, Dr);
