@@ -47,3 +47,42 @@ def test_fullsize_16x16x16x32(oracle_ref, cuda_lib):
     finally:
         S.free()
         R.free()
+
+
+def test_config2_32x32x32x64_three_level(oracle_ref, cuda_lib):
+    """BASELINE.json configs[2] size (32^3 x 64, 3 levels): fine operator against the reference on the same synthetic
+    field, size-independent properties of the device hierarchy (P^H P = 1, Galerkin identity on both coarse levels,
+    gamma5-hermiticity), and a solve to 1e-10 whose residual is checked with the reference's operator."""
+    lat = [64, 32, 32, 32]
+    U = random_gauge_field(lat, seed=20261018, eps=0.3)
+    kw = dict(levels=3, test_vectors=(20, 28), setup_iter=(2, 2), restart=10, m0=-0.1, coarse_block=[2, 2, 2, 2])
+    # the reference only supplies its fine operator here (2-level parameters keep its own setup cheap; no setup is run)
+    R = oracle_ref.Reference(lat, [4, 4, 4, 4], levels=2, test_vectors=(20,), setup_iter=(1,), restart=10, m0=-0.1)
+    S = DDalphaAMG(lat, [4, 4, 4, 4], lib=cuda_lib, **kw)
+    try:
+        pr, ps = R.set_conf(U), S.set_conf(U)
+        assert abs(pr - ps) < 1e-12
+        rng = np.random.default_rng(5)
+        n = S.V * 12
+        u, v = pc.crandom(rng, n), pc.crandom(rng, n)
+        want = R.dw_double(u)
+        Du = S.apply_dw(u)
+        assert pc.rel(want, Du) <= pc.TOL_DOUBLE
+        assert pc.rel(want, S.apply_dw(u, "float")) <= pc.TOL_FLOAT
+        g5 = np.tile(np.repeat([-1.0, 1.0], 6), S.V)
+        lhs, rhs = np.vdot(g5 * Du, v), np.vdot(u, g5 * S.apply_dw(v))
+        assert abs(lhs - rhs) / abs(lhs) < 1e-12
+        S.setup(2)
+        for d in (0, 1):
+            Vc, nc = S.level_shape(d + 1)
+            vc = pc.crandom(rng, Vc * nc, np.complex64)
+            Pv = S.interpolate(d, vc)
+            assert pc.rel(vc, S.restrict(d, Pv)) < 1e-5                                         # P^H P = 1
+            assert pc.rel(S.level_apply(d + 1, vc), S.restrict(d, S.level_apply(d, Pv))) < 2e-5   # P^H D P = D_c
+        b = np.ones(n, dtype=np.complex128)
+        x, res, st = S.solve(b)
+        assert st[0] > 0 and res < 1e-10
+        assert pc.rel(b, R.dw_double(x)) < 1.5e-10
+    finally:
+        S.free()
+        R.free()
