@@ -56,18 +56,27 @@ __device__ __forceinline__ void dw_hop_bwd(const cx<T> *__restrict__ D, const cx
   reconstruct_sub<MU, -1>(g, out);
 }
 
-template <class T, int BLOCK, int MINB>
+// MODE 0: all sites.  MODE 1: only sites whose neighbours are all local (runs while the halo exchange is in flight).
+// MODE 2: the sites of `list` (the rank-boundary sites, after the exchange).
+template <class T, int BLOCK, int MINB, int MODE>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_dw_full(const cx<T> *__restrict__ D, const T *__restrict__ C, const int *__restrict__ nb, const cx<T> *__restrict__ in,
-          cx<T> *__restrict__ out, long V) {
-  const long s = blockIdx.x * (long)BLOCK + threadIdx.x;
-  if (s >= V) return;
+          cx<T> *__restrict__ out, long V, const int *__restrict__ list, long nlist) {
+  const long i0 = blockIdx.x * (long)BLOCK + threadIdx.x;
+  if (MODE == 2 ? (i0 >= nlist) : (i0 >= V)) return;
+  const long s = (MODE == 2) ? (long)list[i0] : i0;
   const int lane = (int)(s & 31);
   const long tile = s >> 5;
   const long tile_s = tile * (12L << 5), tile_u = tile * (36L << 5), tile_c = tile * (72L << 5);
   int n[8];
 #pragma unroll
   for (int d = 0; d < 8; d++) n[d] = __ldg(nb + (long)d * V + s);
+  if (MODE == 1) {
+    bool ghost = false;
+#pragma unroll
+    for (int d = 0; d < 8; d++) ghost = ghost || (n[d] >= V);
+    if (ghost) return;
+  }
 
   cx<T> r[12];
   {
@@ -103,19 +112,28 @@ k_dw_full(const cx<T> *__restrict__ D, const T *__restrict__ C, const int *__res
   for (int c = 0; c < 12; c++) out[tile_s + ((long)c << 5) + lane] = r[c];
 }
 
-template <class T> void dw_apply_fast(const FineOp<T> &op, cx<T> *out, const cx<T> *in) {
-  DDA_ASSERT(op.sh == 5);
+template <class T, int MODE> static void dw_launch(const FineOp<T> &op, cx<T> *out, const cx<T> *in, const int *list, long nlist) {
   const int BLOCK = 128;
-  unsigned grid = (unsigned)((op.V + BLOCK - 1) / BLOCK);
-  if constexpr (sizeof(T) == 8) k_dw_full<T, BLOCK, 2><<<grid, BLOCK, 0, g_stream>>>(op.D, op.C, op.nb, in, out, op.V);
-  else k_dw_full<T, BLOCK, 4><<<grid, BLOCK, 0, g_stream>>>(op.D, op.C, op.nb, in, out, op.V);
+  const long nthreads = (MODE == 2) ? nlist : op.V;
+  if (nthreads <= 0) return;
+  unsigned grid = (unsigned)((nthreads + BLOCK - 1) / BLOCK);
+  if constexpr (sizeof(T) == 8) k_dw_full<T, BLOCK, 2, MODE><<<grid, BLOCK, 0, g_stream>>>(op.D, op.C, op.nb, in, out, op.V, list, nlist);
+  else k_dw_full<T, BLOCK, 4, MODE><<<grid, BLOCK, 0, g_stream>>>(op.D, op.C, op.nb, in, out, op.V, list, nlist);
   g_launch_count++;
 #ifdef DDA_DEBUG_SYNC
   CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());
 #endif
 }
-template void dw_apply_fast<float>(const FineOp<float> &, cf *, const cf *);
-template void dw_apply_fast<double>(const FineOp<double> &, cd *, const cd *);
+
+// mode 0: all sites; 1: interior sites only; 2: the listed (boundary) sites
+template <class T> void dw_apply_fast(const FineOp<T> &op, cx<T> *out, const cx<T> *in, int mode, const int *list, long nlist) {
+  DDA_ASSERT(op.sh == 5);
+  if (mode == 0) dw_launch<T, 0>(op, out, in, nullptr, 0);
+  else if (mode == 1) dw_launch<T, 1>(op, out, in, nullptr, 0);
+  else dw_launch<T, 2>(op, out, in, list, nlist);
+}
+template void dw_apply_fast<float>(const FineOp<float> &, cf *, const cf *, int, const int *, long);
+template void dw_apply_fast<double>(const FineOp<double> &, cd *, const cd *, int, const int *, long);
 
 #endif
 

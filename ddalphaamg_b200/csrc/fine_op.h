@@ -60,6 +60,6 @@ void reals_from_lex(const Geometry &geo, double *dst, const double *src_lex, int
 void reals_to_lex(const Geometry &geo, double *dst_lex, const double *src, int nk);
 
 // optimised full-lattice D_W apply (sm_100a; dw_kernel.cu).  Not available in the emulation build.
-template <class T> void dw_apply_fast(const FineOp<T> &op, cx<T> *out, const cx<T> *in);
+template <class T> void dw_apply_fast(const FineOp<T> &op, cx<T> *out, const cx<T> *in, int mode = 0, const int *list = nullptr, long nlist = 0);
 
 }  // namespace dda

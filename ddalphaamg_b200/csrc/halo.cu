@@ -31,6 +31,37 @@ template <class E> void halo_exchange(const Geometry &g, E *v, int nc, int sh) {
     g_halo_bytes += 2 * (long)bytes;
   }
 }
+#ifndef DDA_HOST_EMU
+static cudaStream_t g_halo_stream = nullptr;
+static cudaEvent_t g_ev_ready = nullptr, g_ev_done = nullptr;
+template <class E> void halo_begin(const Geometry &g, E *v, int nc, int sh) {
+  if (!g.partitioned()) return;
+  if (!g_halo_stream) {
+    int lo = 0, hi = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // the copy/NCCL kernels must get SM slots ahead of the
+    CUDA_CHECK(cudaStreamCreateWithPriority(&g_halo_stream, cudaStreamNonBlocking, hi));   // interior kernel's CTAs
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_ev_ready, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_ev_done, cudaEventDisableTiming));
+  }
+  comm_buffer(0, sizeof(E) * (size_t)g.slab[0] * nc); comm_buffer(1, sizeof(E) * (size_t)g.slab[0] * nc);   // grow (may sync) before forking
+  CUDA_CHECK(cudaEventRecord(g_ev_ready, g_stream));
+  CUDA_CHECK(cudaStreamWaitEvent(g_halo_stream, g_ev_ready, 0));
+  cudaStream_t compute = g_stream;
+  g_stream = g_halo_stream;                 // pack kernel + NCCL calls of halo_exchange go to the second stream
+  halo_exchange<E>(g, v, nc, sh);
+  g_stream = compute;
+  CUDA_CHECK(cudaEventRecord(g_ev_done, g_halo_stream));
+}
+void halo_end(const Geometry &g) {
+  if (!g.partitioned()) return;
+  CUDA_CHECK(cudaStreamWaitEvent(g_stream, g_ev_done, 0));
+}
+#else
+template <class E> void halo_begin(const Geometry &g, E *v, int nc, int sh) { halo_exchange<E>(g, v, nc, sh); }
+void halo_end(const Geometry &) {}
+#endif
+template void halo_begin<cf>(const Geometry &, cf *, int, int);
+template void halo_begin<cd>(const Geometry &, cd *, int, int);
 template void halo_exchange<cf>(const Geometry &, cf *, int, int);
 template void halo_exchange<cd>(const Geometry &, cd *, int, int);
 

@@ -128,12 +128,33 @@ void Geometry::build() {
   std::vector<int> lists[2];
   for (int b = 0; b < nblocks; b++) lists[block_color[b]].push_back(b);
   for (int c = 0; c < 2; c++) { nblk_color[c] = (int)lists[c].size(); d_blocklist[c] = dev_upload(lists[c]); }
+  // sites / blocks on the rank boundary (used to overlap the halo exchange with interior work)
+  {
+    std::vector<char> isb(V, 0);
+    for (int d = 0; d < 8; d++) for (int k : slices[d]) isb[k] = 1;
+    std::vector<int> bl;
+    for (long k = 0; k < V; k++) if (isb[k]) bl.push_back((int)k);
+    nbnd = (long)bl.size();
+    d_bnd = bl.empty() ? nullptr : dev_upload(bl);
+    std::vector<int> li[2], lb[2];
+    for (int b = 0; b < nblocks; b++) {
+      bool on = false;
+      for (int i = 0; i < bs && !on; i++) on = isb[(long)b * bs + i];
+      (on ? lb : li)[block_color[b]].push_back(b);
+    }
+    for (int c = 0; c < 2; c++) {
+      nblk_int[c] = (int)li[c].size(); nblk_bnd[c] = (int)lb[c].size();
+      d_blocklist_int[c] = dev_upload(li[c]); d_blocklist_bnd[c] = dev_upload(lb[c]);
+    }
+  }
 }
 
 void Geometry::destroy() {
   dev_free(d_nb); dev_free(d_blkflag); dev_free(d_aggflag); dev_free(d_lex2nat); dev_free(d_nat2lex);
   dev_free(d_blocklist[0]); dev_free(d_blocklist[1]); dev_free(d_agg2coarse);
   for (int d = 0; d < 8; d++) { dev_free(d_slice[d]); d_slice[d] = nullptr; }
+  dev_free(d_bnd); d_bnd = nullptr;
+  for (int c = 0; c < 2; c++) { dev_free(d_blocklist_int[c]); dev_free(d_blocklist_bnd[c]); d_blocklist_int[c] = d_blocklist_bnd[c] = nullptr; }
   d_nb = nullptr; d_blkflag = d_aggflag = nullptr; d_lex2nat = d_nat2lex = nullptr;
   d_blocklist[0] = d_blocklist[1] = nullptr; d_agg2coarse = nullptr;
 }

@@ -39,6 +39,9 @@ struct Geometry {
   long slab[4] = {0, 0, 0, 0};
   int nbr_rank[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int *d_slice[8] = {};                                 // d<4: local sites with x_mu = 0, d>=4: x_mu = L-1 (native order)
+  int *d_bnd = nullptr; long nbnd = 0;                  // local sites with at least one ghost neighbour (sorted)
+  int *d_blocklist_int[2] = {nullptr, nullptr}, *d_blocklist_bnd[2] = {nullptr, nullptr};   // per colour: blocks without /
+  int nblk_int[2] = {0, 0}, nblk_bnd[2] = {0, 0};       //   with sites on the rank boundary (halo overlap)
   std::vector<int> lex2nat, nat2lex, block_color;
   std::vector<int> h_nb;     // [8][V]
   // device tables

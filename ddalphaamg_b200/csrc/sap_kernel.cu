@@ -417,9 +417,23 @@ void sap_fine_fast(Solver &s, cf *x, const cf *eta, int iters, bool zero_guess) 
       const int nblk = g.nblk_color[col];
       if (nblk == 0) continue;
       const int first = (zero_guess && cyc == 0 && col == 0) ? 1 : 0;
-      if (!first) halo_exchange<cf>(g, x, 12, g.sh);   // block residuals read x of neighbouring blocks on other ranks
-      sap::k_sap_fine<<<nblk, sap::BS, smem, g_stream>>>(L.opf, x, eta, g.d_blocklist[col], biter, first);
-      g_launch_count++;
+      if (first || !g.partitioned()) {
+        sap::k_sap_fine<<<nblk, sap::BS, smem, g_stream>>>(L.opf, x, eta, g.d_blocklist[col], biter, first);
+        g_launch_count++;
+      } else {
+        // block residuals read x of neighbouring blocks on other ranks: exchange the ghost slabs on the second stream
+        // while the blocks away from the rank boundary are solved, then the blocks that touch it
+        halo_begin<cf>(g, x, 12, g.sh);
+        if (g.nblk_int[col] > 0) {
+          sap::k_sap_fine<<<g.nblk_int[col], sap::BS, smem, g_stream>>>(L.opf, x, eta, g.d_blocklist_int[col], biter, 0);
+          g_launch_count++;
+        }
+        halo_end(g);
+        if (g.nblk_bnd[col] > 0) {
+          sap::k_sap_fine<<<g.nblk_bnd[col], sap::BS, smem, g_stream>>>(L.opf, x, eta, g.d_blocklist_bnd[col], biter, 0);
+          g_launch_count++;
+        }
+      }
 #ifdef DDA_DEBUG_SYNC
       CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());
 #endif

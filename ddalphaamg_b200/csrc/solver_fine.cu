@@ -137,22 +137,37 @@ void solver_shift_mass(Solver &s, double new_m0) {
   s.m0_op = new_m0;
 }
 
-template <class T> void dw_apply_fast(const FineOp<T> &op, cx<T> *out, const cx<T> *in);
 
 template <> void solver_apply_dw<double>(Solver &s, cd *out, const cd *in) {
   Level &L = s.lev[0];
-  halo_exchange<cd>(L.geo, const_cast<cd *>(in), 12, L.geo.sh);
 #ifndef DDA_HOST_EMU
-  if (s.use_fast && L.geo.sh == 5) { dw_apply_fast<double>(L.opd, out, in); return; }
+  if (s.use_fast && L.geo.sh == 5) {
+    if (!L.geo.partitioned()) { dw_apply_fast<double>(L.opd, out, in); return; }
+    // interior sites while the ghost slabs travel (second stream), then the rank-boundary sites
+    halo_begin<cd>(L.geo, const_cast<cd *>(in), 12, L.geo.sh);
+    dw_apply_fast<double>(L.opd, out, in, 1);
+    halo_end(L.geo);
+    dw_apply_fast<double>(L.opd, out, in, 2, L.geo.d_bnd, L.geo.nbnd);
+    return;
+  }
 #endif
+  halo_exchange<cd>(L.geo, const_cast<cd *>(in), 12, L.geo.sh);
   fine_apply<double>(L.opd, out, in, sel_all(L.geo.V), HOP_ALL, 0, SELF_C, OUT_SET);
 }
 template <> void solver_apply_dw<float>(Solver &s, cf *out, const cf *in) {
   Level &L = s.lev[0];
-  halo_exchange<cf>(L.geo, const_cast<cf *>(in), 12, L.geo.sh);
 #ifndef DDA_HOST_EMU
-  if (s.use_fast && L.geo.sh == 5) { dw_apply_fast<float>(L.opf, out, in); return; }
+  if (s.use_fast && L.geo.sh == 5) {
+    if (!L.geo.partitioned()) { dw_apply_fast<float>(L.opf, out, in); return; }
+    // interior sites while the ghost slabs travel (second stream), then the rank-boundary sites
+    halo_begin<cf>(L.geo, const_cast<cf *>(in), 12, L.geo.sh);
+    dw_apply_fast<float>(L.opf, out, in, 1);
+    halo_end(L.geo);
+    dw_apply_fast<float>(L.opf, out, in, 2, L.geo.d_bnd, L.geo.nbnd);
+    return;
+  }
 #endif
+  halo_exchange<cf>(L.geo, const_cast<cf *>(in), 12, L.geo.sh);
   fine_apply<float>(L.opf, out, in, sel_all(L.geo.V), HOP_ALL, 0, SELF_C, OUT_SET);
 }
 
