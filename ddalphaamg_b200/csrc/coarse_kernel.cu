@@ -19,6 +19,7 @@
 // because the reference stores S packed Hermitian; bench.py reports against the SURVEY figure).
 #include "coarse_op.h"
 #include <cstdint>
+#include <vector>
 
 namespace dda {
 
@@ -202,6 +203,155 @@ __global__ void k_coarse_combine(CoarseOp op, cf *__restrict__ out, const cf *__
     }
   }
   out[i] = acc;
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// Fused SAP block solve on an intermediate level: ONE CTA per Schwarz block runs all block_iter minimal-residual steps
+//   Dr = D_block r ;  alpha = <Dr,r>/<Dr,Dr> ;  e += alpha r ;  r -= alpha Dr          and finally   x += e.
+// Reference counterparts: red_black_schwarz_PRECISION with the coarse block operator (schwarz_generic.c:1260-1431,
+// coarse_block_operator_PRECISION coarse_operator_generic.c:208-236), local_minres_PRECISION (linsolve_generic.c:985-1029).
+// The block vectors (bs x n complex each) stay in shared memory; the block operator is streamed once per MR step
+// through the same TMA ring as k_coarse_full: the self coupling of every site and every in-block link exactly once
+// (forward product for the link's source site, daggered product for its target site), partial sums added to Dr with
+// shared-memory atomics.  The generic path needs 4 launches per MR step and reads every in-block link twice.
+struct SapJob { int type, i, j, pad; };        // type 0: self coupling of local site i; 1+mu: link i -> j = i+mu
+
+template <int STAGES>
+__global__ void __launch_bounds__(128)
+k_coarse_sap_mr(CoarseOp op, cf *__restrict__ x, const cf *__restrict__ rin, const int *__restrict__ blocklist, int bs,
+                int biter, const SapJob *__restrict__ jobs, int njobs, int G) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int n = op.n, nn = n * n, nh = n / 2, P = n / 2, ch = n / G;
+  const int len = bs * n;
+  cf *Ms = reinterpret_cast<cf *>(smem_raw);                    // [STAGES][n*n]
+  cf *rv = Ms + (size_t)STAGES * nn;                            // block residual
+  cf *rg = rv + len;                                            // gamma5 * residual
+  cf *ev = rg + len;                                            // accumulated correction
+  cf *Dr = ev + len;                                            // D_block r
+  float *red = reinterpret_cast<float *>(Dr + len);             // [4][4]
+  SapJob *sj = reinterpret_cast<SapJob *>(red + 16);            // [njobs]
+  uint64_t *full = reinterpret_cast<uint64_t *>(sj + njobs);    // [STAGES]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int grp = tid / P, p = tid - grp * P;
+  const bool active = grp < G;
+  const uint32_t bytes = (uint32_t)(nn * sizeof(cf));
+  const long base = (long)blocklist[blockIdx.x] * bs;
+  const int total = biter * njobs;
+  for (int q = tid; q < njobs; q += 128) sj[q] = jobs[q];
+  for (int q = tid; q < len; q += 128) {
+    const cf v = rin[base * n + q];
+    rv[q] = v; rg[q] = ((q % n) < nh) ? v : -v; ev[q] = cf(0.f, 0.f); Dr[q] = cf(0.f, 0.f);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int jj) {
+    const SapJob jb = sj[jj % njobs];
+    const cf *src = (jb.type == 0) ? op.S + (base + jb.i) * nn : op.F + ((base + jb.i) * 4 + (jb.type - 1)) * nn;
+    const int st = jj % STAGES;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&full[st], bytes);
+    tma_bulk_g2s(Ms + (size_t)st * nn, src, bytes, &full[st]);
+  };
+  if (tid == 0) for (int jj = 0; jj < STAGES && jj < total; jj++) issue(jj);
+  const float sgc = (2 * p < nh) ? 1.f : -1.f;                  // gamma5 sign of the thread's daggered output columns
+
+  int jj = 0;
+  for (int it = 0; it < biter; it++) {
+    for (int q = 0; q < njobs; q++, jj++) {
+      const int st = jj % STAGES;
+      const SapJob jb = sj[q];
+      mbar_wait(&full[st], (uint32_t)((jj / STAGES) & 1));
+      const cf *M = Ms + (size_t)st * nn;
+      if (active) {
+        {                                 // forward: Dr[i] += M v,  v = r[i] (self coupling) or r[j] (link)
+          const int src = (jb.type == 0) ? jb.i : jb.j;
+          const float4 *v4 = reinterpret_cast<const float4 *>(rv + src * n + grp * ch);
+          const cf *Mb = M + (size_t)(grp * ch) * n + 2 * p;
+          float f0r = 0.f, f0i = 0.f, f1r = 0.f, f1i = 0.f;
+#pragma unroll 2
+          for (int cc = 0; cc < ch; cc += 2) {
+            const float4 v = v4[cc >> 1];
+            const float4 m0 = *reinterpret_cast<const float4 *>(Mb + (size_t)cc * n);
+            const float4 m1 = *reinterpret_cast<const float4 *>(Mb + (size_t)(cc + 1) * n);
+            f0r += m0.x * v.x - m0.y * v.y; f0i += m0.x * v.y + m0.y * v.x;
+            f1r += m0.z * v.x - m0.w * v.y; f1i += m0.z * v.y + m0.w * v.x;
+            f0r += m1.x * v.z - m1.y * v.w; f0i += m1.x * v.w + m1.y * v.z;
+            f1r += m1.z * v.z - m1.w * v.w; f1i += m1.z * v.w + m1.w * v.z;
+          }
+          float *d = reinterpret_cast<float *>(Dr + jb.i * n + 2 * p);
+          atomicAdd(d, f0r); atomicAdd(d + 1, f0i); atomicAdd(d + 2, f1r); atomicAdd(d + 3, f1i);
+        }
+        if (jb.type > 0) {                // daggered: Dr[j] += gamma5 M^H gamma5 r[i]
+          const cf *wv_ = rg + jb.i * n;
+          const cf *M0 = M + (size_t)(2 * p) * n, *M1 = M0 + n;
+          float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;
+          int ip = grp * (ch >> 1) + p; if (ip >= P) ip -= P;
+#pragma unroll 2
+          for (int i = 0; i < (ch >> 1); i++) {
+            const float4 wv = *reinterpret_cast<const float4 *>(wv_ + 2 * ip);
+            const float4 m0 = *reinterpret_cast<const float4 *>(M0 + 2 * ip);
+            const float4 m1 = *reinterpret_cast<const float4 *>(M1 + 2 * ip);
+            a0r += m0.x * wv.x + m0.y * wv.y; a0i += m0.x * wv.y - m0.y * wv.x;
+            a0r += m0.z * wv.z + m0.w * wv.w; a0i += m0.z * wv.w - m0.w * wv.z;
+            a1r += m1.x * wv.x + m1.y * wv.y; a1i += m1.x * wv.y - m1.y * wv.x;
+            a1r += m1.z * wv.z + m1.w * wv.w; a1i += m1.z * wv.w - m1.w * wv.z;
+            ip++; if (ip == P) ip = 0;
+          }
+          float *d = reinterpret_cast<float *>(Dr + jb.j * n + 2 * p);
+          atomicAdd(d, sgc * a0r); atomicAdd(d + 1, sgc * a0i); atomicAdd(d + 2, sgc * a1r); atomicAdd(d + 3, sgc * a1i);
+        }
+      }
+      __syncthreads();
+      if (tid == 0 && jj + STAGES < total) issue(jj + STAGES);
+    }
+    // alpha = <Dr,r>/<Dr,Dr> over the block (local_xy_over_xx, linalg_generic.c:158-169)
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+    for (int q = tid; q < len; q += 128) {
+      const cf a = Dr[q], b = rv[q];
+      p0 += a.re * b.re + a.im * b.im; p1 += a.re * b.im - a.im * b.re; p2 += a.re * a.re + a.im * a.im;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+    }
+    if (lane == 0) { red[4 * w] = p0; red[4 * w + 1] = p1; red[4 * w + 2] = p2; }
+    __syncthreads();
+    p0 = red[0] + red[4] + red[8] + red[12]; p1 = red[1] + red[5] + red[9] + red[13]; p2 = red[2] + red[6] + red[10] + red[14];
+    cf alpha(0.f, 0.f);
+    if (p2 > 1e-30f) alpha = cf(p0 / p2, p1 / p2);
+    for (int q = tid; q < len; q += 128) {
+      cf e = ev[q], r = rv[q];
+      const cf d = Dr[q];
+      fma_(e, alpha, r); fms_(r, alpha, d);
+      ev[q] = e; rv[q] = r; rg[q] = ((q % n) < nh) ? r : -r; Dr[q] = cf(0.f, 0.f);
+    }
+    __syncthreads();
+  }
+  for (int q = tid; q < len; q += 128) x[base * n + q] += ev[q];
+}
+
+bool coarse_sap_mr_fast(const CoarseOp &op, cf *x, const cf *r, const int *d_blocklist, int nblk, int bs, int biter,
+                        const int *d_jobs, int njobs) {
+  const int n = op.n;
+  if (n > 64 || n < 8 || (n & 3) || nblk <= 0 || biter <= 0 || !d_jobs || njobs <= 0) return false;
+  int G = 128 / (n / 2);
+  while (G > 1 && n % (2 * G) != 0) G--;
+  if (n % (2 * G) != 0) return false;
+  const int stages = 2;
+  const size_t nn = (size_t)n * n, len = (size_t)bs * n;
+  const size_t smem = stages * nn * sizeof(cf) + 4 * len * sizeof(cf) + 16 * sizeof(float) + njobs * sizeof(SapJob) + 8 * sizeof(uint64_t);
+  if (smem > 200 * 1024) return false;
+  static size_t attr = 0;
+  if (smem > attr) { CUDA_CHECK(cudaFuncSetAttribute(k_coarse_sap_mr<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  k_coarse_sap_mr<2><<<nblk, 128, smem, g_stream>>>(op, x, r, d_blocklist, bs, biter, reinterpret_cast<const SapJob *>(d_jobs), njobs, G);
+  g_launch_count++;
+#ifdef DDA_DEBUG_SYNC
+  CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());
+#endif
+  return true;
 }
 
 int g_coarse_stages = 0;   // 0: default; 3 / 4: force the depth of the TMA ring (tuning knob, env DDA_COARSE_STAGES)

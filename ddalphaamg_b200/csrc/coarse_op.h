@@ -35,5 +35,10 @@ void coarse_invert_odd_self(CoarseOp &op);
 // optimised full-lattice apply (sm_100a only; coarse_kernel.cu); Z: scratch of 4*n complex per site.  Returns false
 // when the shape is not supported (caller falls back to coarse_apply).
 bool coarse_apply_fast(const CoarseOp &op, cf *out, const cf *in, cf *Z);
+// fused SAP block solve of an intermediate level: for every listed block, biter minimal-residual steps on the block
+// operator starting from the block residual r, then x += e (sm_100a only; coarse_kernel.cu).  d_jobs / njobs: the
+// level's block-operator job list (Geometry::d_sapjobs).
+bool coarse_sap_mr_fast(const CoarseOp &op, cf *x, const cf *r, const int *d_blocklist, int nblk, int bs, int biter,
+                        const int *d_jobs, int njobs);
 
 }  // namespace dda

@@ -120,6 +120,7 @@ void Geometry::build() {
     }
   }
   d_nb = dev_upload(h_nb);
+  h_blkflag = bf;
   d_blkflag = dev_upload(bf);
   d_aggflag = dev_upload(af);
   for (int d = 0; d < 8; d++) d_slice[d] = slices[d].empty() ? nullptr : dev_upload(slices[d]);
@@ -128,6 +129,16 @@ void Geometry::build() {
   std::vector<int> lists[2];
   for (int b = 0; b < nblocks; b++) lists[block_color[b]].push_back(b);
   for (int c = 0; c < 2; c++) { nblk_color[c] = (int)lists[c].size(); d_blocklist[c] = dev_upload(lists[c]); }
+  // job list of the block operator (fused coarse SAP kernel): blocks are contiguous site ranges with identical
+  // internal structure, block 0 (sites 0..bs-1) defines the list
+  if (!block_eo && !last && nblocks > 0) {
+    std::vector<int> jobs;
+    for (int i = 0; i < bs; i++) { jobs.push_back(0); jobs.push_back(i); jobs.push_back(i); jobs.push_back(0); }
+    for (int i = 0; i < bs; i++) for (int m = 0; m < 4; m++)
+      if (!((bf[i] >> m) & 1)) { jobs.push_back(1 + m); jobs.push_back(i); jobs.push_back(h_nb[(long)m * V + i]); jobs.push_back(0); }
+    nsapjobs = (int)(jobs.size() / 4);
+    d_sapjobs = dev_upload(jobs);
+  }
   // sites / blocks on the rank boundary (used to overlap the halo exchange with interior work)
   {
     std::vector<char> isb(V, 0);
@@ -154,6 +165,7 @@ void Geometry::destroy() {
   dev_free(d_blocklist[0]); dev_free(d_blocklist[1]); dev_free(d_agg2coarse);
   for (int d = 0; d < 8; d++) { dev_free(d_slice[d]); d_slice[d] = nullptr; }
   dev_free(d_bnd); d_bnd = nullptr;
+  dev_free(d_sapjobs); d_sapjobs = nullptr; nsapjobs = 0;
   for (int c = 0; c < 2; c++) { dev_free(d_blocklist_int[c]); dev_free(d_blocklist_bnd[c]); d_blocklist_int[c] = d_blocklist_bnd[c] = nullptr; }
   d_nb = nullptr; d_blkflag = d_aggflag = nullptr; d_lex2nat = d_nat2lex = nullptr;
   d_blocklist[0] = d_blocklist[1] = nullptr; d_agg2coarse = nullptr;

@@ -44,6 +44,9 @@ struct Geometry {
   int nblk_int[2] = {0, 0}, nblk_bnd[2] = {0, 0};       //   with sites on the rank boundary (halo overlap)
   std::vector<int> lex2nat, nat2lex, block_color;
   std::vector<int> h_nb;     // [8][V]
+  std::vector<unsigned char> h_blkflag;   // [V]
+  int *d_sapjobs = nullptr; int nsapjobs = 0;   // block operator as a job list {type, i, j, 0}: type 0 = self coupling of
+                                                // block-local site i, 1+mu = in-block link i -> j (same for every block)
   // device tables
   int *d_nb = nullptr;                 // [8][V] dir 0..3 = +T,+Z,+Y,+X ; 4..7 = -T,-Z,-Y,-X
   unsigned char *d_blkflag = nullptr;  // bit d: neighbour d is outside the Schwarz block

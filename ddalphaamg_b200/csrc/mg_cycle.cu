@@ -141,6 +141,10 @@ void mg_smoother(Solver &s, int depth, cf *phi, const cf *eta, int iters, bool z
         lv_apply(L, e, a, so, HOP_NONE, 0, SELF_CINV, OUT_SET);
       } else {
         // plain MR on the block operator (coarse_block_operator, coarse_operator_generic.c:208-236)
+#ifndef DDA_HOST_EMU
+        if (depth > 0 && s.use_fast && biter > 0 &&
+            coarse_sap_mr_fast(L.cop, x, r, list, nblk, bs, biter, g.d_sapjobs, g.nsapjobs)) continue;   // fused: MR steps and x += e
+#endif
         for (int it = 0; it < biter; it++) {
           lv_apply(L, Dr, r, sb, HOP_INBLOCK, 0, SELF_C, OUT_SET);
           block_mr_step(L, list, nblk, bs, e, r, Dr, it == 0);
