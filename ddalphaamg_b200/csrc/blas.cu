@@ -45,12 +45,60 @@ template <class T> void vmulti_axpy(cx<T> *y, cx<T> *const *V, const cd *coef, i
   });
 }
 
+// out[k] = <V[k], w>, k < m.  One pass per chunk of 8 basis vectors: every thread reads w[i] once and the 8 V[k][i],
+// so the traffic is (m + ceil(m/8)) vectors instead of 2 m (one segmented reduction per vector re-reads w each time).
+// Reference: process_multi_inner_product_PRECISION (linalg_generic.c:107-154).
+#ifndef DDA_HOST_EMU
+template <class T, int KB> __global__ void __launch_bounds__(256) k_multi_dot(PtrArr<T> pa, int k0, int kn, const cx<T> *__restrict__ w, long n, double *out) {
+  double ar[KB], ai[KB];
+#pragma unroll
+  for (int k = 0; k < KB; k++) { ar[k] = 0.0; ai[k] = 0.0; }
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const cx<T> b = w[i];
+#pragma unroll
+    for (int k = 0; k < KB; k++) if (k < kn) {
+      const cx<T> a = pa.p[k0 + k][i];
+      ar[k] += (double)a.re * b.re + (double)a.im * b.im;
+      ai[k] += (double)a.re * b.im - (double)a.im * b.re;
+    }
+  }
+  __shared__ double sm[2 * KB][8];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < KB; k++) {
+    double x = ar[k], y = ai[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { x += __shfl_xor_sync(0xffffffffu, x, o); y += __shfl_xor_sync(0xffffffffu, y, o); }
+    if (lane == 0) { sm[2 * k][wp] = x; sm[2 * k + 1][wp] = y; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * KB) {
+    double v = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) v += sm[threadIdx.x][q];
+    const int k = threadIdx.x >> 1;
+    if (k < kn) atomicAdd(&out[2 * (k0 + k) + (threadIdx.x & 1)], v);
+  }
+}
+#endif
+
 template <class T> void vmulti_dot(cd *out, cx<T> *const *V, int m, const cx<T> *w, long n) {
   DDA_ASSERT(m <= MAXV);
   if (m <= 0) return;
   PtrArr<T> pa;
   for (int k = 0; k < m; k++) pa.p[k] = V[k];
   double *buf = red_buf();
+#ifndef DDA_HOST_EMU
+  if (n >= (1L << 16)) {
+    dev_zero(buf, sizeof(double) * 2 * m);
+    const int KB = 8;
+    long blocks = std::min<long>((n + 255) / 256, 148L * 8);
+    for (int k0 = 0; k0 < m; k0 += KB) {
+      k_multi_dot<T, KB><<<(unsigned)blocks, 256, 0, g_stream>>>(pa, k0, std::min(KB, m - k0), w, n, buf);
+      g_launch_count++;
+    }
+  } else
+#endif
   launch_reduce<2>(m, n, DLAMBDA(long seg, long i, double *acc) {
     cx<T> a = pa.p[seg][i], b = w[i];
     acc[0] += (double)a.re * b.re + (double)a.im * b.im;
@@ -60,6 +108,25 @@ template <class T> void vmulti_dot(cd *out, cx<T> *const *V, int m, const cx<T> 
   comm_allreduce_sum(buf, 2 * m);
   d2h(h, buf, sizeof(double) * 2 * m);
   for (int k = 0; k < m; k++) out[k] = cd(h[2 * k], h[2 * k + 1]);
+}
+
+// y += sign * sum_k coef[k] V[k] and ||y_new||^2 in the same pass (the Arnoldi orthogonalisation followed by the norm of
+// the new direction, linsolve_generic.c:859-880: one read of y less than saxpy + norm)
+template <class T> double vmulti_axpy_norm2(cx<T> *y, cx<T> *const *V, const cd *coef, int m, int sign, long n) {
+  DDA_ASSERT(m <= MAXV);
+  PtrArr<T> pa; CoefArr ca;
+  for (int k = 0; k < m; k++) { pa.p[k] = V[k]; ca.re[k] = sign * coef[k].re; ca.im[k] = sign * coef[k].im; }
+  double *buf = red_buf();
+  launch_reduce<1>(1, n, DLAMBDA(long seg, long i, double *acc) {
+    (void)seg;
+    cx<T> v = y[i];
+    for (int k = 0; k < m; k++) fma_(v, cx<T>((T)ca.re[k], (T)ca.im[k]), pa.p[k][i]);
+    y[i] = v;
+    acc[0] += (double)v.re * v.re + (double)v.im * v.im;
+  }, buf);
+  comm_allreduce_sum(buf, 1);
+  double h; d2h(&h, buf, sizeof(double));
+  return h;
 }
 
 template <class T> void vmulti_dot_norm(cd *out, cx<T> *const *V, int m, const cx<T> *w, long n) {
@@ -101,6 +168,7 @@ template <class T> double vnorm2(const cx<T> *x, long n) {
   template void vsub<T>(cx<T> *, const cx<T> *, const cx<T> *, long); \
   template void vadd<T>(cx<T> *, const cx<T> *, const cx<T> *, long); \
   template void vmulti_axpy<T>(cx<T> *, cx<T> *const *, const cd *, int, int, long); \
+  template double vmulti_axpy_norm2<T>(cx<T> *, cx<T> *const *, const cd *, int, int, long); \
   template cd vdot<T>(const cx<T> *, const cx<T> *, long); \
   template double vnorm2<T>(const cx<T> *, long); \
   template void vmulti_dot<T>(cd *, cx<T> *const *, int, const cx<T> *, long); \

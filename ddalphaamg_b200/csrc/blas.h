@@ -17,6 +17,8 @@ template <class T> void vadd(cx<T> *z, const cx<T> *x, const cx<T> *y, long n); 
 template <class T, class S> void vcast(cx<T> *y, const cx<S> *x, long n);                   // precision cast
 // y -= sum_k coef[k] V[k]   (coef on the host; k < m <= 64); reference vector_PRECISION_multi_saxpy
 template <class T> void vmulti_axpy(cx<T> *y, cx<T> *const *V, const cd *coef, int m, int sign, long n);
+// same update, returns sum |y_new|^2 (fused pass; synchronises)
+template <class T> double vmulti_axpy_norm2(cx<T> *y, cx<T> *const *V, const cd *coef, int m, int sign, long n);
 
 // host-returning reductions (synchronise the stream); the sum over ranks (comm_allreduce_sum, NCCL) is applied to the
 // device buffer before the single device->host copy

@@ -63,8 +63,7 @@ template <class T> struct Fgmres {
         std::vector<cd> hcol(j + 2);
         vmulti_dot(hcol.data(), V.data(), j + 1, w, n);
         for (int i = 0; i <= j; i++) h(i, j) = hcol[i];
-        vmulti_axpy(w, V.data(), hcol.data(), j + 1, -1, n);
-        double hn = std::sqrt(vnorm2(w, n));
+        double hn = std::sqrt(vmulti_axpy_norm2(w, V.data(), hcol.data(), j + 1, -1, n));
         h(j + 1, j) = cd(hn, 0);
         if (hn > 1e-15) vscale(V[j + 1], w, 1.0 / hn, n);
         if (hn > tol / 10) {
