@@ -216,39 +216,49 @@ __global__ void k_coarse_combine(CoarseOp op, cf *__restrict__ out, const cf *__
 // shared-memory atomics.  The generic path needs 4 launches per MR step and reads every in-block link twice.
 struct SapJob { int type, i, j, pad; };        // type 0: self coupling of local site i; 1+mu: link i -> j = i+mu
 
-template <int STAGES>
-__global__ void __launch_bounds__(128)
+// TEAMS x 128 threads: every team of 128 streams its own share of the jobs (job q -> team q % TEAMS) through its own ring;
+// all teams add into the same Dr.  TEAMS = 4 when a rank has fewer blocks than SMs (strong-scaling limit), else 1.
+template <int STAGES, int TEAMS>
+__global__ void __launch_bounds__(128 * TEAMS)
 k_coarse_sap_mr(CoarseOp op, cf *__restrict__ x, const cf *__restrict__ rin, const int *__restrict__ blocklist, int bs,
                 int biter, const SapJob *__restrict__ jobs, int njobs, int G) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = op.n, nn = n * n, nh = n / 2, P = n / 2, ch = n / G;
   const int len = bs * n;
-  cf *Ms = reinterpret_cast<cf *>(smem_raw);                    // [STAGES][n*n]
-  cf *rv = Ms + (size_t)STAGES * nn;                            // block residual
+  cf *Ms0 = reinterpret_cast<cf *>(smem_raw);                   // [TEAMS][STAGES][n*n]
+  cf *rv = Ms0 + (size_t)TEAMS * STAGES * nn;                   // block residual
   cf *rg = rv + len;                                            // gamma5 * residual
   cf *ev = rg + len;                                            // accumulated correction
   cf *Dr = ev + len;                                            // D_block r
-  float *red = reinterpret_cast<float *>(Dr + len);             // [4][4]
-  SapJob *sj = reinterpret_cast<SapJob *>(red + 16);            // [njobs]
-  uint64_t *full = reinterpret_cast<uint64_t *>(sj + njobs);    // [STAGES]
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  float *red = reinterpret_cast<float *>(Dr + len);             // [16 warps][4]
+  SapJob *sj = reinterpret_cast<SapJob *>(red + 64);            // [njobs]
+  uint64_t *full0 = reinterpret_cast<uint64_t *>(sj + njobs);   // [TEAMS][STAGES]
+  const int NT = 128 * TEAMS;
+  const int gtid = threadIdx.x, team = gtid >> 7, tid = gtid & 127, lane = tid & 31, w = gtid >> 5;
+  cf *Ms = Ms0 + (size_t)team * STAGES * nn;
+  uint64_t *full = full0 + team * STAGES;
   const int grp = tid / P, p = tid - grp * P;
   const bool active = grp < G;
   const uint32_t bytes = (uint32_t)(nn * sizeof(cf));
   const long base = (long)blocklist[blockIdx.x] * bs;
-  const int total = biter * njobs;
-  for (int q = tid; q < njobs; q += 128) sj[q] = jobs[q];
-  for (int q = tid; q < len; q += 128) {
+  const int myjobs = (njobs - team + TEAMS - 1) / TEAMS;        // jobs team, team + TEAMS, ... of every MR step
+  const int total = biter * myjobs;
+  for (int q = gtid; q < njobs; q += NT) sj[q] = jobs[q];
+  for (int q = gtid; q < len; q += NT) {
     const cf v = rin[base * n + q];
     rv[q] = v; rg[q] = ((q % n) < nh) ? v : -v; ev[q] = cf(0.f, 0.f); Dr[q] = cf(0.f, 0.f);
   }
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+  if (gtid == 0) {
+    for (int s = 0; s < STAGES * TEAMS; s++) mbar_init(&full0[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto issue = [&](int jj) {
-    const SapJob jb = sj[jj % njobs];
+  auto team_sync = [&]() {
+    if (TEAMS == 1) __syncthreads();
+    else asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
+  };
+  auto issue = [&](int jj) {                                     // jj-th job of this team
+    const SapJob jb = sj[(jj % myjobs) * TEAMS + team];
     const cf *src = (jb.type == 0) ? op.S + (base + jb.i) * nn : op.F + ((base + jb.i) * 4 + (jb.type - 1)) * nn;
     const int st = jj % STAGES;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -260,9 +270,9 @@ k_coarse_sap_mr(CoarseOp op, cf *__restrict__ x, const cf *__restrict__ rin, con
 
   int jj = 0;
   for (int it = 0; it < biter; it++) {
-    for (int q = 0; q < njobs; q++, jj++) {
+    for (int q = 0; q < myjobs; q++, jj++) {
       const int st = jj % STAGES;
-      const SapJob jb = sj[q];
+      const SapJob jb = sj[q * TEAMS + team];
       mbar_wait(&full[st], (uint32_t)((jj / STAGES) & 1));
       const cf *M = Ms + (size_t)st * nn;
       if (active) {
@@ -304,12 +314,13 @@ k_coarse_sap_mr(CoarseOp op, cf *__restrict__ x, const cf *__restrict__ rin, con
           atomicAdd(d, sgc * a0r); atomicAdd(d + 1, sgc * a0i); atomicAdd(d + 2, sgc * a1r); atomicAdd(d + 3, sgc * a1i);
         }
       }
-      __syncthreads();
+      team_sync();
       if (tid == 0 && jj + STAGES < total) issue(jj + STAGES);
     }
+    if (TEAMS > 1) __syncthreads();                              // all teams' contributions are in Dr
     // alpha = <Dr,r>/<Dr,Dr> over the block (local_xy_over_xx, linalg_generic.c:158-169)
     float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-    for (int q = tid; q < len; q += 128) {
+    for (int q = gtid; q < len; q += NT) {
       const cf a = Dr[q], b = rv[q];
       p0 += a.re * b.re + a.im * b.im; p1 += a.re * b.im - a.im * b.re; p2 += a.re * a.re + a.im * a.im;
     }
@@ -319,10 +330,12 @@ k_coarse_sap_mr(CoarseOp op, cf *__restrict__ x, const cf *__restrict__ rin, con
     }
     if (lane == 0) { red[4 * w] = p0; red[4 * w + 1] = p1; red[4 * w + 2] = p2; }
     __syncthreads();
-    p0 = red[0] + red[4] + red[8] + red[12]; p1 = red[1] + red[5] + red[9] + red[13]; p2 = red[2] + red[6] + red[10] + red[14];
+    p0 = p1 = p2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4 * TEAMS; k++) { p0 += red[4 * k]; p1 += red[4 * k + 1]; p2 += red[4 * k + 2]; }
     cf alpha(0.f, 0.f);
     if (p2 > 1e-30f) alpha = cf(p0 / p2, p1 / p2);
-    for (int q = tid; q < len; q += 128) {
+    for (int q = gtid; q < len; q += NT) {
       cf e = ev[q], r = rv[q];
       const cf d = Dr[q];
       fma_(e, alpha, r); fms_(r, alpha, d);
@@ -330,7 +343,7 @@ k_coarse_sap_mr(CoarseOp op, cf *__restrict__ x, const cf *__restrict__ rin, con
     }
     __syncthreads();
   }
-  for (int q = tid; q < len; q += 128) x[base * n + q] += ev[q];
+  for (int q = gtid; q < len; q += NT) x[base * n + q] += ev[q];
 }
 
 bool coarse_sap_mr_fast(const CoarseOp &op, cf *x, const cf *r, const int *d_blocklist, int nblk, int bs, int biter,
@@ -340,13 +353,22 @@ bool coarse_sap_mr_fast(const CoarseOp &op, cf *x, const cf *r, const int *d_blo
   int G = 128 / (n / 2);
   while (G > 1 && n % (2 * G) != 0) G--;
   if (n % (2 * G) != 0) return false;
-  const int stages = 2;
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const size_t nn = (size_t)n * n, len = (size_t)bs * n;
-  const size_t smem = stages * nn * sizeof(cf) + 4 * len * sizeof(cf) + 16 * sizeof(float) + njobs * sizeof(SapJob) + 8 * sizeof(uint64_t);
+  int teams = (nblk <= 2 * sms) ? 4 : 1;            // few blocks per rank: more threads per block instead of more blocks per SM
+  if (const char *e = getenv("DDA_SAP_TEAMS")) { const int t = atoi(e); if (t == 1 || t == 4) teams = t; }   // test / tuning override
+  const size_t smem = (size_t)teams * 2 * nn * sizeof(cf) + 4 * len * sizeof(cf) + 64 * sizeof(float) + njobs * sizeof(SapJob) + 8 * sizeof(uint64_t);
   if (smem > 200 * 1024) return false;
-  static size_t attr = 0;
-  if (smem > attr) { CUDA_CHECK(cudaFuncSetAttribute(k_coarse_sap_mr<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
-  k_coarse_sap_mr<2><<<nblk, 128, smem, g_stream>>>(op, x, r, d_blocklist, bs, biter, reinterpret_cast<const SapJob *>(d_jobs), njobs, G);
+  static size_t attr1 = 0, attr4 = 0;
+  const SapJob *jb = reinterpret_cast<const SapJob *>(d_jobs);
+  if (teams == 4) {
+    if (smem > attr4) { CUDA_CHECK(cudaFuncSetAttribute(k_coarse_sap_mr<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr4 = smem; }
+    k_coarse_sap_mr<2, 4><<<nblk, 512, smem, g_stream>>>(op, x, r, d_blocklist, bs, biter, jb, njobs, G);
+  } else {
+    if (smem > attr1) { CUDA_CHECK(cudaFuncSetAttribute(k_coarse_sap_mr<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr1 = smem; }
+    k_coarse_sap_mr<2, 1><<<nblk, 128, smem, g_stream>>>(op, x, r, d_blocklist, bs, biter, jb, njobs, G);
+  }
   g_launch_count++;
 #ifdef DDA_DEBUG_SYNC
   CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());

@@ -9,7 +9,10 @@ import parity_common as pc
 pytestmark = pytest.mark.gpu
 
 
-def test_three_level_kcycle_vs_reference(oracle_ref, cuda_lib):
+@pytest.mark.parametrize("teams", ["1", "4"])
+def test_three_level_kcycle_vs_reference(oracle_ref, cuda_lib, teams, monkeypatch):
+    # both thread-team configurations of the fused coarse-level SAP kernel (chosen by block count in production)
+    monkeypatch.setenv("DDA_SAP_TEAMS", teams)
     dims, plaq, U = read_conf(CONF8)
     kw = dict(levels=3, test_vectors=(20, 28), setup_iter=(1, 1), restart=50, coarse_block=[2, 2, 2, 2])
     R = oracle_ref.Reference(dims, [2, 2, 2, 2], **kw)
