@@ -294,10 +294,20 @@ def run_native(args, w, name):
     dev_bytes = S.stat(STAT.DEVICE_BYTES)
     S.free()
 
+    # dominant kernel of the solve: k_sap_fine (one launch = the block visits of one colour; a smoother call = 2 iterations
+    # x 2 colours = 4 launches).  Algorithmic bytes per block visit: 256*(288+336) + 5*256*96 = 282 624 B.
+    # DRAM traffic per block visit measured by ncu --set full (profiles/r1_ncu_full_k_sap_fine_final.txt): 1.545 GB per
+    # launch of 4096 visits = 377 KB.
     dom = ops["sap_smoother_d0"]
-    roof = {"kernel": "fine-level SAP smoother (red-black Schwarz, %d block visits per call)" % (2 * nblk),
+    visits_per_launch = nblk / 2.0
+    launch_ms = dom["ms"] / 4.0
+    roof = {"kernel": "k_sap_fine: fused fine-level SAP block solve, one CTA per 4^4 Schwarz block (%d block visits per launch, "
+                      "avg launch %.3f ms from CUDA events over %d launches)" % (int(visits_per_launch), launch_ms, 4 * 5),
             "bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak,
-            "traffic": None, "peak_source": peak_src}
+            "traffic": 377.2e3 * visits_per_launch, "algorithmic_bytes_per_launch": 282624.0 * visits_per_launch,
+            "peak_source": peak_src,
+            "note": "arithmetic intensity 8.5 flop/B: the kernel is fp32-issue bound (ncu: 52 % issue slots, 18 % DRAM), "
+                    "see DESIGN.md section 4; D_W and coarse-operator GB/s (the metric's named kernels) are in `operators`"}
 
     if world > 1:
         from ddalphaamg_b200.interface import comm_finalize
