@@ -51,7 +51,7 @@ CPU_SAMPLE = {2: [16, 8, 8, 8], 3: [16, 16, 16, 16]}
 
 def solver_kwargs(w):
     kw = dict(levels=w["levels"], test_vectors=w["test_vectors"], setup_iter=w["setup_iter"], restart=10,
-              max_restart=50, m0=w["m0"], csw=1.0, tol=1e-10, mixed_precision=1)
+              max_restart=50, m0=w["m0"], csw=1.0, tol=1e-10, mixed_precision=w.get("mixed_precision", 2))
     if w["levels"] > 2:
         kw["coarse_block"] = w.get("coarse_block", [2, 2, 2, 2])
     return kw
@@ -317,10 +317,10 @@ def run_native(args, w, name):
 
     out = {"metric": METRIC, "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * sec, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-           "dtype": "f64 outer / f32 cycle", "data": "synthetic",
+           "dtype": "f64 restarts + f32 Arnoldi/cycle (mixed precision %d)" % w.get("mixed_precision", 2), "data": "synthetic",
            "config": {"workload": name, "detail": w["config"], "lattice_TZYX": lat, "local_lattice_TZYX": [lt] + lat[1:],
                       "partition": "T split over %d GPU(s), NCCL send/recv halos + allreduce" % world, "levels": w["levels"],
-                      "test_vectors": list(w["test_vectors"]), "m0": w["m0"], "csw": 1.0, "tol": 1e-10,
+                      "test_vectors": list(w["test_vectors"]), "mixed_precision": w.get("mixed_precision", 2), "m0": w["m0"], "csw": 1.0, "tol": 1e-10,
                       "gauge": "U=exp(i*0.3*H), H Gaussian traceless Hermitian, seed 20261018, plaquette %.6f" % plaq,
                       "l2": "working set %.1f GB per solve >> 126 MB L2 (inputs larger than L2, no flush)" % (dev_bytes / 1e9),
                       "iterations": its, "setup_seconds_untimed": t_setup},
@@ -350,8 +350,12 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--m0", type=float, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mixed-precision", type=int, default=2, choices=[1, 2],
+                    help="reference parameter `mixed precision` (both arms): 2 = fgmres_MP, the reference's default "
+                         "(init.c:581-962); 1 = double outer FGMRES")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
+    w["mixed_precision"] = args.mixed_precision
     if args.m0 is not None:
         w["m0"] = args.m0
     if args.impl == "reference":

@@ -290,6 +290,7 @@ void dd_alpha_amg_free(void) {
   Solver &s = A->s;
   if (s.setup_done && s.nlev > 1) mg_free(s);
   s.outer.release();
+  s.outer_mp.release();
   solver_free_fine(s);
   delete A; A = nullptr; g_solver = nullptr;
 }

@@ -103,4 +103,105 @@ template <class T> struct Fgmres {
   }
 };
 
+// Mixed-precision FGMRES ("mixed precision: 2"): restarts, true residual and solution in double; Arnoldi basis, operator
+// and preconditioner in float with double-accumulated inner products; an inner cycle ends after a residual reduction of
+// max(tol, 1e-5).  Behaviour follows fgmres_MP / arnoldi_step_MP / compute_solution_MP (linsolve.c:153-424) and
+// fgmres_MP_struct_alloc (linsolve.c:31-50).  The float vectors are already in the level's native order, so the
+// reference's trans / trans_back permutations reduce to precision casts.
+struct FgmresMP {
+  long n = 0;
+  int m = 0, max_restart = 0;
+  double tol = 0, sp_tol = 0;
+  bool allocated = false;
+  std::vector<cf *> V, Z;
+  cf *w = nullptr;
+  cd *r = nullptr;
+  std::vector<cd> H, gamma, c, s, y;
+  std::function<void(cd *, const cd *)> op_d;
+  std::function<void(cf *, const cf *)> op_f, prec_f;
+  int last_iter = 0;
+  double last_relres = 0;
+
+  void alloc(long n_, int m_, int max_restart_, double tol_, bool flexible, long nalloc_ = 0) {
+    release();
+    n = n_; m = m_; max_restart = max_restart_; tol = tol_; sp_tol = std::max(tol_, 1e-5);
+    const long na = nalloc_ > n_ ? nalloc_ : n_;
+    V.resize(m + 1); for (auto &v : V) v = dev_alloc<cf>(na);
+    if (flexible) { Z.resize(m); for (auto &z : Z) z = dev_alloc<cf>(na); }
+    w = dev_alloc<cf>(na); r = dev_alloc<cd>(na);
+    H.assign((size_t)(m + 1) * m, cd(0, 0)); gamma.assign(m + 1, cd(0, 0)); c.assign(m, cd(0, 0)); s.assign(m, cd(0, 0)); y.assign(m, cd(0, 0));
+    allocated = true;
+  }
+  void release() {
+    for (auto v : V) dev_free(v);
+    for (auto z : Z) dev_free(z);
+    V.clear(); Z.clear();
+    dev_free(w); dev_free(r); w = nullptr; r = nullptr; allocated = false;
+  }
+  cd &h(int i, int j) { return H[(size_t)j * (m + 1) + i]; }
+
+  int solve(cd *x, const cd *b, bool zero_guess) {
+    DDA_ASSERT(allocated && op_d && op_f);
+    sp_tol = std::max(tol, 1e-5);
+    int iter = 0, finish = 0, j = -1;
+    double norm_r0 = 1, gamma_jp1 = 1;
+    for (int ol = 0; ol < max_restart && !finish; ol++) {
+      if (ol == 0 && zero_guess) vcopy(r, b, n);
+      else { op_d(r, x); vsub(r, b, r, n); }
+      const double g0 = std::sqrt(vnorm2(r, n));
+      gamma[0] = cd(g0, 0);
+      if (ol == 0) norm_r0 = g0;
+      if (g0 == 0.0) { if (ol == 0 && zero_guess) vzero(x, n); last_relres = 0; break; }
+      vcast(V[0], r, n);
+      vscale(V[0], V[0], 1.0 / g0, n);
+      j = -1;
+      for (int il = 0; il < m && !finish; il++) {
+        j = il; iter++;
+        const cf *zj = V[j];
+        if (prec_f) { prec_f(Z[j], V[j]); zj = Z[j]; }
+        op_f(w, zj);
+        std::vector<cd> hcol(j + 2);
+        vmulti_dot(hcol.data(), V.data(), j + 1, w, n);
+        for (int i = 0; i <= j; i++) h(i, j) = hcol[i];
+        const double hn = std::sqrt(vmulti_axpy_norm2(w, V.data(), hcol.data(), j + 1, -1, n));
+        h(j + 1, j) = cd(hn, 0);
+        if (hn > 1e-15) {
+          vscale(V[j + 1], w, 1.0 / hn, n);
+          for (int i = 0; i < j; i++) {
+            cd beta = (-s[i]) * h(i, j) + c[i] * h(i + 1, j);
+            h(i, j) = conj(c[i]) * h(i, j) + conj(s[i]) * h(i + 1, j);
+            h(i + 1, j) = beta;
+          }
+          const double bn = std::sqrt(norm2(h(j, j)) + norm2(h(j + 1, j)));
+          s[j] = cd(h(j + 1, j).re / bn, h(j + 1, j).im / bn); c[j] = cd(h(j, j).re / bn, h(j, j).im / bn);
+          gamma[j + 1] = (-s[j]) * gamma[j]; gamma[j] = conj(c[j]) * gamma[j];
+          h(j, j) = cd(bn, 0); h(j + 1, j) = cd(0, 0);
+          gamma_jp1 = std::sqrt(norm2(gamma[j + 1]));
+          if (gamma_jp1 / norm_r0 < tol || gamma_jp1 / norm_r0 > 1e5) {
+            finish = 1;
+            if (gamma_jp1 / norm_r0 > 1e5) fprintf(stderr, "dd_alpha_amg_b200: divergence of fgmres_MP, iter = %d\n", iter);
+          }
+          if (gamma_jp1 / g0 < sp_tol) break;
+        } else { finish = 1; }
+      }
+      if (j >= 0) {
+        for (int i = j; i >= 0; i--) {
+          cd yi = gamma[i];
+          for (int k = i + 1; k <= j; k++) yi -= h(i, k) * y[k];
+          const double d = norm2(h(i, i)); const cd hi = h(i, i);
+          y[i] = cd((yi.re * hi.re + yi.im * hi.im) / d, (yi.im * hi.re - yi.re * hi.im) / d);
+        }
+        std::vector<cf *> &B = prec_f ? Z : V;
+        vzero(w, n);
+        vmulti_axpy(w, B.data(), y.data(), j + 1, +1, n);
+        vcast(r, w, n);
+        if (ol == 0) vcopy(x, r, n); else vadd(x, x, r, n);
+      }
+      last_relres = gamma_jp1 / norm_r0;
+    }
+    last_iter = iter;
+    return iter;
+  }
+};
+
 }  // namespace dda

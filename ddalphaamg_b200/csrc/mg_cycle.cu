@@ -248,13 +248,14 @@ void mg_preconditioner(Solver &s, cd *out, const cd *in) {
 
 double mg_solve(Solver &s, cd *x, const cd *b, double tol, int *status) {
   s.coarse_iter_count = 0;
-  s.outer.tol = tol;
-  int it = s.outer.solve(x, b, true);
+  int it;
+  if (s.outer_mp.allocated) { s.outer_mp.tol = tol; it = s.outer_mp.solve(x, b, true); }
+  else { s.outer.tol = tol; it = s.outer.solve(x, b, true); }
   s.iter_count = it;
   // true residual (reference -DFGMRES_RESTEST, linsolve_generic.c:351-357)
   Level &L = s.lev[0];
   const long n = L.geo.vlen();
-  cd *w = s.outer.w;
+  cd *w = s.outer_mp.allocated ? s.outer_mp.r : s.outer.w;
   solver_apply_dw<double>(s, w, x);
   vsub(w, b, w, n);
   double nr = std::sqrt(vnorm2(w, n)), nb = std::sqrt(vnorm2(b, n));

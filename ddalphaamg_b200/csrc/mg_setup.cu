@@ -229,10 +229,21 @@ void mg_setup(Solver &s, int setup_iters) {
   // outer solver
   {
     Solver *sp = &s;
-    s.outer.alloc(L0.geo.vlen(), p.restart, p.max_restart, p.tol, p.method > 0 && p.num_levels > 1, L0.geo.valloc());
-    s.outer.op = [sp](cd *out, const cd *in) { solver_apply_dw<double>(*sp, out, in); };
-    if (p.method > 0 && p.num_levels > 1) s.outer.prec = [sp](cd *out, const cd *in) { mg_preconditioner(*sp, out, in); };
-    else s.outer.prec = nullptr;
+    const bool mg = p.method > 0 && p.num_levels > 1;
+    if (p.mixed_precision == 2) {
+      s.outer.release();
+      s.outer_mp.alloc(L0.geo.vlen(), p.restart, p.max_restart, p.tol, mg, L0.geo.valloc());
+      s.outer_mp.op_d = [sp](cd *out, const cd *in) { solver_apply_dw<double>(*sp, out, in); };
+      s.outer_mp.op_f = [sp](cf *out, const cf *in) { solver_apply_dw<float>(*sp, out, in); };
+      if (mg) s.outer_mp.prec_f = [sp](cf *out, const cf *in) { mg_vcycle(*sp, 0, out, in, true); };
+      else s.outer_mp.prec_f = nullptr;
+    } else {
+      s.outer_mp.release();
+      s.outer.alloc(L0.geo.vlen(), p.restart, p.max_restart, p.tol, mg, L0.geo.valloc());
+      s.outer.op = [sp](cd *out, const cd *in) { solver_apply_dw<double>(*sp, out, in); };
+      if (mg) s.outer.prec = [sp](cd *out, const cd *in) { mg_preconditioner(*sp, out, in); };
+      else s.outer.prec = nullptr;
+    }
   }
   if (p.method <= 0 || p.num_levels < 2) { s.nlev = 1; s.setup_done = true; return; }
   mg_alloc(s);

@@ -43,7 +43,8 @@ struct Solver {
   bool fine_alloc = false, conf_set = false, setup_done = false;
   double plaq = 0.0;
   double m0_op = 0.0;                     // mass currently folded into the clover diagonal
-  Fgmres<double> outer;                   // outer double-precision FGMRES
+  Fgmres<double> outer;                   // outer double-precision FGMRES ("mixed precision: 0/1")
+  FgmresMP outer_mp;                      // mixed-precision outer solver ("mixed precision: 2", linsolve.c:153)
   cd *xb = nullptr, *xx = nullptr;        // device source / solution of the outer solve (native layout)
   cd *lexbuf = nullptr;                   // device staging buffer, lexicographic (36 complex per site)
   long coarse_iter_count = 0, iter_count = 0;

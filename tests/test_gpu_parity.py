@@ -82,3 +82,4 @@ def test_golden_vectors_4x4x4x4(cuda_lib):
         assert abs(int(st[0]) - int(g["solve_iters"][0])) <= 1 and res < 1e-10
     finally:
         S.free()
+

@@ -118,3 +118,4 @@ def test_synthetic_field_generator_is_su3():
     M = (U[..., 0] + 1j * U[..., 1]).reshape(-1, 3, 3)
     assert np.abs(M @ np.conj(np.swapaxes(M, 1, 2)) - np.eye(3)).max() < 1e-13
     assert np.abs(np.linalg.det(M) - 1.0).max() < 1e-13
+
