@@ -362,6 +362,68 @@ class DDalphaAMG:
         self.L.dd_alpha_amg_init(p)
         self.emulated = bool(self.L.dda_info(INFO.EMULATION, 0))
 
+    @classmethod
+    def from_struct(cls, lattice, block, levels=2, test_vectors=(20, 28), setup_iter=(4, 3), post_smooth=(2, 2),
+                    block_iter=(4, 4), m0=-0.5, csw=1.0, bc=2, coarse_iter=100, coarse_restart=5, coarse_tol=5e-2,
+                    coarse_lattice=None, coarse_block=None, lib=None):
+        """The struct route dd_alpha_amg_init_external_threading (include/dd_alpha_amg.h:44, src/dd_alpha_amg.c:135-173):
+        geometry from dd_alpha_amg_parameters, lattice arrays in X,Y,Z,T order (reversed inside, init.c:821-823)."""
+        self = cls.__new__(cls)
+        self.L = load_library(lib)
+        self.global_lattice = [int(x) for x in lattice]
+        self.lattice = list(self.global_lattice)
+        self.V = int(np.prod(self.lattice))
+        self._tmp = None
+        p = Par()
+        ap = p.amg_params
+        ap.number_of_levels = levels
+        lat = list(lattice)
+        blk = list(block)
+        for i in range(levels):
+            for m in range(4):
+                ap.global_lattice[i][3 - m] = lat[m]
+                ap.local_lattice[i][3 - m] = lat[m]
+                ap.block_lattice[i][3 - m] = blk[m] if i < levels - 1 else 1
+            ap.mg_basis_vectors[i] = test_vectors[min(i, len(test_vectors) - 1)]
+            ap.setup_iterations[i] = setup_iter[min(i, len(setup_iter) - 1)]
+            ap.post_smooth_iterations[i] = post_smooth[min(i, len(post_smooth) - 1)]
+            ap.post_smooth_block_iterations[i] = block_iter[min(i, len(block_iter) - 1)]
+            if i < levels - 1:
+                lat = coarse_lattice if (i == 0 and coarse_lattice) else [a // b for a, b in zip(lat, blk)]
+                blk = coarse_block or [2, 2, 2, 2]
+        ap.coarse_grid_iterations = coarse_iter
+        ap.coarse_grid_maximum_number_of_restarts = coarse_restart
+        ap.coarse_grid_tolerance = coarse_tol
+        ap.solver_mass = m0
+        ap.setup_mass = m0
+        ap.c_sw = csw
+        p.conf_index_fct = CONF_INDEX_FCT(0)
+        p.vector_index_fct = VECTOR_INDEX_FCT(0)
+        p.global_time = GLOBAL_TIME_FCT(0)
+        p.bc, p.m0, p.csw, p.setup_m0 = bc, m0, csw, m0
+        self._par = p
+        self.L.dd_alpha_amg_init_external_threading(p, 1, 1)
+        self.emulated = bool(self.L.dda_info(INFO.EMULATION, 0))
+        return self
+
+    def update_parameters(self, solver_mass, post_smooth=(2, 2, 2, 2), block_iter=(4, 4, 4, 4), setup_iter=(4, 3, 2, 2)):
+        """dd_alpha_amg_update_parameters (include/dd_alpha_amg.h:56, init.c:1139-1148): iteration counts + mass shift."""
+        ap = AmgParameters()
+        for i in range(MAX_MG_LEVELS):
+            ap.post_smooth_iterations[i] = post_smooth[i]
+            ap.post_smooth_block_iterations[i] = block_iter[i]
+            ap.setup_iterations[i] = setup_iter[i]
+        ap.solver_mass = solver_mass
+        self.L.dd_alpha_amg_update_parameters(C.byref(ap))
+
+    def gauge_pointer(self):
+        """numpy view of the host mirror of D = U/2 (dd_alpha_amg_get_gauge_pointer, dirac.c:171-176)."""
+        ptr = self.L.dd_alpha_amg_get_gauge_pointer()
+        return np.ctypeslib.as_array(ptr, shape=(self.V * 72,))
+
+    def fields_updated(self):
+        self.L.dd_alpha_amg_fields_updated()
+
     # ---- reference interface
     def set_conf(self, U):
         U = np.ascontiguousarray(U, dtype=np.float64)
