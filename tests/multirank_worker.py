@@ -32,7 +32,10 @@ def main():
     t0, t1 = rank * lt, (rank + 1) * lt
     local = [lt] + dims[1:]
     Vs = int(np.prod(dims[1:]))
-    if levels == 2:
+    if levels == 2 and world > 2:
+        block = [2, 2, 2, 2]      # local T extent 8 / world = 2: one block in T per rank, coarse local T extent 1
+        kw = dict(levels=2, test_vectors=(12,), setup_iter=(2,), restart=20)
+    elif levels == 2:
         block = [4, 4, 4, 4]
         kw = dict(levels=2, test_vectors=(20,), setup_iter=(2,), restart=10)
     else:

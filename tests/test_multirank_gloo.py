@@ -27,7 +27,7 @@ def run_ranks(lib, backend, levels, tmp_path, world=2, timeout=900):
     procs, outs = [], []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
-                   MASTER_PORT=str(port), OMP_NUM_THREADS="4")
+                   MASTER_PORT=str(port), OMP_NUM_THREADS=str(max(1, (os.cpu_count() or 4) // world)))
         o = str(tmp_path / ("rank%d.json" % r))
         outs.append(o)
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "multirank_worker.py"), lib, backend, o, str(levels)],
@@ -60,3 +60,8 @@ def check(results, imported_tol_iters=1):
 @pytest.mark.parametrize("levels", [2, 3])
 def test_two_ranks_split_T(emu_lib, oracle_ref, tmp_path, levels):
     check(run_ranks(emu_lib, "gloo", levels, tmp_path))
+
+
+def test_four_ranks_split_T(emu_lib, oracle_ref, tmp_path):
+    """Four ranks: the +T and -T neighbours of a rank are different processes (with two ranks they coincide)."""
+    check(run_ranks(emu_lib, "gloo", 2, tmp_path, world=4), imported_tol_iters=1)
