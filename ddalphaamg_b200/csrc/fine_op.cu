@@ -63,13 +63,16 @@ static HD M3 m3_mul_bd(const M3 &A, const M3 &B) { M3 C; for (int i = 0; i < 3; 
 static HD M3 m3_mul_ad(const M3 &A, const M3 &B) { M3 C; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { cd s(0.0, 0.0); for (int k = 0; k < 3; k++) fmac_(s, A.a[3 * k + i], B.a[3 * k + j]); C.a[3 * i + j] = s; } return C; }  // A^dag B
 static HD M3 m3_mul_adbd(const M3 &A, const M3 &B) { M3 C; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { cd s(0.0, 0.0); for (int k = 0; k < 3; k++) fma_(s, conj(A.a[3 * k + i]), conj(B.a[3 * j + k])); C.a[3 * i + j] = s; } return C; }  // A^dag B^dag
 
-// neighbour-table walk: the shift along d1 (never a partitioned direction) is applied first, then the shift along d0
-// (may lead into a ghost slab, whose sites have no table entries of their own).  Only T (direction 0) is partitioned
-// and callers pass mu < nu as (d0, d1) = (mu, nu).
-struct CloverGeom { const int *nb; long V; int sh; };
+// neighbour-table walk from site s: shift s1 along d1, then s0 along d0 (d < 0: no shift).  Intermediate sites may be
+// ghost sites of a partitioned direction: they have their own neighbour table (Geometry::d_nbg), and the ghost slabs are
+// built so that the corner sites exist (lattice.cu).
+struct CloverGeom { const int *nb, *nbg; long V, Vg; int sh; };
+static HD long cg_step(const CloverGeom &g, long s, int d) {
+  return s < g.V ? g.nb[(long)d * g.V + s] : g.nbg[(long)d * g.Vg + (s - g.V)];
+}
 static HD long cg_site(const CloverGeom &g, long s, int d0, int s0, int d1, int s1) {
-  if (d1 >= 0) s = g.nb[(long)(s1 > 0 ? d1 : 4 + d1) * g.V + s];
-  if (d0 >= 0) s = g.nb[(long)(s0 > 0 ? d0 : 4 + d0) * g.V + s];
+  if (d1 >= 0) s = cg_step(g, s, s1 > 0 ? d1 : 4 + d1);
+  if (d0 >= 0) s = cg_step(g, s, s0 > 0 ? d0 : 4 + d0);
   return s;
 }
 static HD M3 cg_link(const CloverGeom &g, const cd *D, long s, int mu) {
@@ -89,7 +92,7 @@ static GammaTab gamma_tab() {
 }
 
 void fine_build_clover(const Geometry &geo, const cd *D, double *C, double m0, double csw, double *plaq_out) {
-  CloverGeom cg; cg.nb = geo.d_nb; cg.V = geo.V; cg.sh = geo.sh;
+  CloverGeom cg; cg.nb = geo.d_nb; cg.nbg = geo.d_nbg; cg.V = geo.V; cg.Vg = geo.Vg; cg.sh = geo.sh;
   const GammaTab gt = gamma_tab();
   const Lay lc = {72, geo.sh};
   double *d_plaq = dev_alloc<double>(1);

@@ -43,7 +43,9 @@ template <class E> void halo_begin(const Geometry &g, E *v, int nc, int sh) {
     CUDA_CHECK(cudaEventCreateWithFlags(&g_ev_ready, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&g_ev_done, cudaEventDisableTiming));
   }
-  comm_buffer(0, sizeof(E) * (size_t)g.slab[0] * nc); comm_buffer(1, sizeof(E) * (size_t)g.slab[0] * nc);   // grow (may sync) before forking
+  long smax = 0;
+  for (int m = 0; m < 4; m++) smax = std::max(smax, g.slab[m]);
+  comm_buffer(0, sizeof(E) * (size_t)smax * nc); comm_buffer(1, sizeof(E) * (size_t)smax * nc);   // grow (may sync) before forking
   CUDA_CHECK(cudaEventRecord(g_ev_ready, g_stream));
   CUDA_CHECK(cudaStreamWaitEvent(g_halo_stream, g_ev_ready, 0));
   cudaStream_t compute = g_stream;

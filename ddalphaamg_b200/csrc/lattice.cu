@@ -72,52 +72,77 @@ void Geometry::build() {
     nat2lex[k] = (int)i;
     coord[4 * (long)k + 0] = t; coord[4 * (long)k + 1] = z; coord[4 * (long)k + 2] = y; coord[4 * (long)k + 3] = x;
   }
-  // ghost slabs of the partitioned directions: slab-local index = rank of the site inside its slice in lexicographic order
+  // Ghost slabs of the partitioned directions, processed in the order T, Z, Y, X.  The slab of direction m is taken
+  // over the lattice already EXTENDED by the ghosts of the directions processed before it, so after the exchanges (same
+  // order) the corner sites x +- T +- Z that the clover term needs are present as well.  Slab-local order = lexicographic
+  // in the (extended) coordinates: identical on every rank (the native order of the coarsest level depends on the parity
+  // of the rank's origin).  Slices may therefore contain ghost sites of earlier directions.
   Vg = 0;
-  std::vector<int> slice_rank[8];
   std::vector<int> slices[8];
+  const int E[4] = {L[0] + 2, L[1] + 2, L[2] + 2, L[3] + 2};
+  auto eidx = [&](const int *c) { return (((long)(c[0] + 1) * E[1] + (c[1] + 1)) * E[2] + (c[2] + 1)) * E[3] + (c[3] + 1); };
+  std::vector<int> ext((size_t)E[0] * E[1] * E[2] * E[3], -1);
+  for (long k = 0; k < V; k++) ext[eidx(&coord[4 * k])] = (int)k;
+  std::vector<int> gcoord;                      // coordinates of the ghost sites, 4 per site
+  int lo[4] = {0, 0, 0, 0}, hi[4] = {L[0] - 1, L[1] - 1, L[2] - 1, L[3] - 1};
   for (int m = 0; m < 4; m++) {
     slab[m] = 0; gh_off[m] = gh_off[4 + m] = -1;
     if (P[m] <= 1) continue;
-    slab[m] = V / L[m];
-    if (sh > 0) DDA_ASSERT(slab[m] % (1L << sh) == 0);
     for (int side = 0; side < 2; side++) {
-      int d = side == 0 ? m : 4 + m;            // slices[m]: x_m = 0 ; slices[4+m]: x_m = L-1
-      int want = side == 0 ? 0 : L[m] - 1;
-      slice_rank[d].assign(V, -1);
-      // lexicographic order of the slice: identical on every rank (the native order of the coarsest level depends on
-      // the parity of the rank's origin)
-      for (long i = 0; i < V; i++) { long k = lex2nat[i]; if (coord[4 * k + m] == want) { slice_rank[d][k] = (int)slices[d].size(); slices[d].push_back((int)k); } }
-      DDA_ASSERT((long)slices[d].size() == slab[m]);
+      const int d = side == 0 ? m : 4 + m;       // +m ghost <- neighbour's x_m = 0 slice ; -m ghost <- its x_m = L-1 slice
+      const int src = side == 0 ? 0 : L[m] - 1, dst = side == 0 ? L[m] : -1;
+      gh_off[d] = V + Vg;
+      int c[4];
+      long cnt = 0;
+      for (c[0] = lo[0]; c[0] <= hi[0]; c[0]++) for (c[1] = lo[1]; c[1] <= hi[1]; c[1]++)
+        for (c[2] = lo[2]; c[2] <= hi[2]; c[2]++) for (c[3] = lo[3]; c[3] <= hi[3]; c[3]++) {
+          if (c[m] != lo[m]) continue;           // the cross-section: every other coordinate once
+          int cs[4] = {c[0], c[1], c[2], c[3]}, cg[4] = {c[0], c[1], c[2], c[3]};
+          cs[m] = src; cg[m] = dst;
+          const int si = ext[eidx(cs)];
+          DDA_ASSERT(si >= 0);
+          slices[d].push_back(si);
+          ext[eidx(cg)] = (int)(V + Vg + cnt);
+          for (int q = 0; q < 4; q++) gcoord.push_back(cg[q]);
+          cnt++;
+        }
+      if (side == 0) slab[m] = cnt; else DDA_ASSERT(slab[m] == cnt);
+      Vg += cnt;
     }
-    gh_off[m] = V + Vg; Vg += slab[m];
-    gh_off[4 + m] = V + Vg; Vg += slab[m];
+    if (sh > 0) DDA_ASSERT(slab[m] % (1L << sh) == 0);
+    lo[m] = -1; hi[m] = L[m];
     int cp[4] = {pc[0], pc[1], pc[2], pc[3]}, cm[4] = {pc[0], pc[1], pc[2], pc[3]};
     cp[m] = (pc[m] + 1) % P[m]; cm[m] = (pc[m] + P[m] - 1) % P[m];
     nbr_rank[m] = ((cp[0] * P[1] + cp[1]) * P[2] + cp[2]) * P[3] + cp[3];
     nbr_rank[4 + m] = ((cm[0] * P[1] + cm[1]) * P[2] + cm[2]) * P[3] + cm[3];
   }
   DDA_ASSERT(V + Vg < (1L << 31));
+  // neighbour of the (possibly ghost) site with coordinates c in direction d; -1 if it is not part of the extended lattice
+  auto neighbour = [&](const int *c, int d) {
+    const int m = d & 3, sgn = d < 4 ? +1 : -1;
+    int q[4] = {c[0], c[1], c[2], c[3]};
+    q[m] += sgn;
+    if (P[m] <= 1) q[m] = (q[m] + L[m]) % L[m];
+    else if (q[m] < -1 || q[m] > L[m]) return -1;
+    return ext[eidx(q)];
+  };
   h_nb.assign(8 * V, 0);
   std::vector<unsigned char> bf(V, 0), af(V, 0);
   for (long k = 0; k < V; k++) {
     int *c = &coord[4 * k];
+    for (int d = 0; d < 8; d++) { h_nb[(long)d * V + k] = neighbour(c, d); DDA_ASSERT(h_nb[(long)d * V + k] >= 0); }
     for (int m = 0; m < 4; m++) {
-      int cp[4] = {c[0], c[1], c[2], c[3]}, cm[4] = {c[0], c[1], c[2], c[3]};
-      cp[m] = (c[m] + 1) % L[m]; cm[m] = (c[m] + L[m] - 1) % L[m];
-      h_nb[(long)m * V + k] = lex2nat[lex(cp[0], cp[1], cp[2], cp[3])];
-      h_nb[(long)(4 + m) * V + k] = lex2nat[lex(cm[0], cm[1], cm[2], cm[3])];
-      if (P[m] > 1) {
-        // the periodic image inside the local lattice has the same transverse coordinates as the true neighbour on
-        // the adjacent rank: +mu ghost slab = neighbour's x_m = 0 slice, -mu slab = neighbour's x_m = L-1 slice
-        if (c[m] == L[m] - 1) h_nb[(long)m * V + k] = (int)(gh_off[m] + slice_rank[m][h_nb[(long)m * V + k]]);
-        if (c[m] == 0) h_nb[(long)(4 + m) * V + k] = (int)(gh_off[4 + m] + slice_rank[4 + m][h_nb[(long)(4 + m) * V + k]]);
-      }
       if (c[m] % Bq[m] == Bq[m] - 1) bf[k] |= (unsigned char)(1u << m);
       if (c[m] % Bq[m] == 0) bf[k] |= (unsigned char)(1u << (4 + m));
       if (c[m] % Aq[m] == Aq[m] - 1) af[k] |= (unsigned char)(1u << m);
       if (c[m] % Aq[m] == 0) af[k] |= (unsigned char)(1u << (4 + m));
     }
+  }
+  // neighbour table of the ghost sites (only the clover construction walks from ghost sites)
+  {
+    std::vector<int> nbg((size_t)8 * (Vg > 0 ? Vg : 1), -1);
+    for (long gi = 0; gi < Vg; gi++) for (int d = 0; d < 8; d++) nbg[(long)d * Vg + gi] = neighbour(&gcoord[4 * gi], d);
+    d_nbg = dev_upload(nbg);
   }
   d_nb = dev_upload(h_nb);
   h_blkflag = bf;
@@ -142,7 +167,7 @@ void Geometry::build() {
   // sites / blocks on the rank boundary (used to overlap the halo exchange with interior work)
   {
     std::vector<char> isb(V, 0);
-    for (int d = 0; d < 8; d++) for (int k : slices[d]) isb[k] = 1;
+    for (long k = 0; k < V; k++) for (int d = 0; d < 8; d++) if (h_nb[(long)d * V + k] >= V) isb[k] = 1;
     std::vector<int> bl;
     for (long k = 0; k < V; k++) if (isb[k]) bl.push_back((int)k);
     nbnd = (long)bl.size();
@@ -165,6 +190,7 @@ void Geometry::destroy() {
   dev_free(d_blocklist[0]); dev_free(d_blocklist[1]); dev_free(d_agg2coarse);
   for (int d = 0; d < 8; d++) { dev_free(d_slice[d]); d_slice[d] = nullptr; }
   dev_free(d_bnd); d_bnd = nullptr;
+  dev_free(d_nbg); d_nbg = nullptr;
   dev_free(d_sapjobs); d_sapjobs = nullptr; nsapjobs = 0;
   for (int c = 0; c < 2; c++) { dev_free(d_blocklist_int[c]); dev_free(d_blocklist_bnd[c]); d_blocklist_int[c] = d_blocklist_bnd[c] = nullptr; }
   d_nb = nullptr; d_blkflag = d_aggflag = nullptr; d_lex2nat = d_nat2lex = nullptr;

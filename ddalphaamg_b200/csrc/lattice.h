@@ -32,13 +32,16 @@ struct Geometry {
   // ---- domain decomposition (one process per GPU): process grid, this rank's coordinates, ghost slabs.
   // Vector arrays of the level hold V local sites followed by Vg ghost sites: for every partitioned direction mu a
   // +mu slab (copy of the +mu neighbour rank's x_mu = 0 slice) and a -mu slab (the -mu neighbour's x_mu = L-1 slice);
-  // the neighbour table points into the slabs.  Reference: ghost shell of data_layout.c:24-40, ghost_generic.c.
+  // the neighbour table points into the slabs.  Directions are processed in the order T, Z, Y, X and the slab of a
+  // direction spans the lattice extended by the slabs of the earlier ones (corner sites for the clover term).
+  // Reference: ghost shell of data_layout.c:24-40, ghost_generic.c.
   int P[4] = {1, 1, 1, 1}, pc[4] = {0, 0, 0, 0};
   long Vg = 0;
   long gh_off[8] = {-1, -1, -1, -1, -1, -1, -1, -1};   // first site index (>= V) of slab d (d<4: +mu, d>=4: -mu)
   long slab[4] = {0, 0, 0, 0};
   int nbr_rank[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int *d_slice[8] = {};                                 // d<4: local sites with x_mu = 0, d>=4: x_mu = L-1 (native order)
+  int *d_nbg = nullptr;                                 // [8][Vg] neighbour table of the ghost sites (-1: not present)
   int *d_bnd = nullptr; long nbnd = 0;                  // local sites with at least one ghost neighbour (sorted)
   int *d_blocklist_int[2] = {nullptr, nullptr}, *d_blocklist_bnd[2] = {nullptr, nullptr};   // per colour: blocks without /
   int nblk_int[2] = {0, 0}, nblk_bnd[2] = {0, 0};       //   with sites on the rank boundary (halo overlap)

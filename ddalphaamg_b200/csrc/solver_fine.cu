@@ -20,7 +20,6 @@ void solver_process_grid(Solver &s, int depth, Geometry &g) {
             "(call dda_comm_init before dd_alpha_amg_init)\n", depth, g.P[0], g.P[1], g.P[2], g.P[3], np, g_comm.size);
     fatal("geometry", __FILE__, __LINE__);
   }
-  if (g.P[1] != 1 || g.P[2] != 1 || g.P[3] != 1) fatal("only the T direction can be partitioned in this build", __FILE__, __LINE__);
   for (int m = 0; m < 4; m++) DDA_ASSERT(g.P[m] == p.global_lattice[0][m] / p.local_lattice[0][m]);
   int r = g_comm.rank;
   for (int m = 3; m >= 0; m--) { g.pc[m] = r % g.P[m]; r /= g.P[m]; }

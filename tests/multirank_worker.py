@@ -27,12 +27,12 @@ def main():
     dist.init_process_group(backend, rank=rank, world_size=world)
     comm_init(lib)
     dims, plaq, U = read_conf(os.path.join(ROOT, "tests", "golden", "conf_8x8x8x8b6.0000id3n1"))
-    T = dims[0]
-    lt = T // world
-    t0, t1 = rank * lt, (rank + 1) * lt
-    local = [lt] + dims[1:]
-    Vs = int(np.prod(dims[1:]))
-    if levels == 2 and world > 2:
+    # process grid PT x PZ (argv[5] = "PT,PZ", default: all ranks along T); rank = cT * PZ + cZ (T slowest)
+    PT, PZ = (int(v) for v in sys.argv[5].split(",")) if len(sys.argv) > 5 else (world, 1)
+    assert PT * PZ == world
+    cT, cZ = rank // PZ, rank % PZ
+    local = [dims[0] // PT, dims[1] // PZ] + dims[2:]
+    if levels == 2 and (world > 2 or PZ > 1):
         block = [2, 2, 2, 2]      # local T extent 8 / world = 2: one block in T per rank, coarse local T extent 1
         kw = dict(levels=2, test_vectors=(12,), setup_iter=(2,), restart=20)
     elif levels == 2:
@@ -46,10 +46,15 @@ def main():
     R.set_conf(U)
     R.setup(kw["setup_iter"][0])
     S = DDalphaAMG(dims, block, lib=lib, local_lattice=local, **kw)
-    out["plaq_err"] = abs(S.set_conf(U[t0:t1]) - plaq)
+    def part(a4, c_t, c_z):    # this (or another) rank's part of an array whose first four axes are the global T,Z,Y,X
+        lt, lz = a4.shape[0] // PT, a4.shape[1] // PZ
+        return np.ascontiguousarray(a4[c_t * lt:(c_t + 1) * lt, c_z * lz:(c_z + 1) * lz])
 
-    def loc(v, nc):     # local part of a global lexicographic vector with nc entries per site
-        return np.ascontiguousarray(v.reshape(-1, nc)[t0 * (v.size // nc // T):t1 * (v.size // nc // T)]).reshape(-1)
+    out["plaq_err"] = abs(S.set_conf(part(U, cT, cZ)) - plaq)
+
+    def loc(v, nc, depth=0):     # local part of a global lexicographic vector of level `depth` with nc entries per site
+        g = [R.info(7 + m, depth) for m in range(4)]
+        return part(v.reshape(g + [nc]), cT, cZ).reshape(-1)
 
     rng = np.random.default_rng(4321)
     v = pc.crandom(rng, R.V * 12)
@@ -66,10 +71,14 @@ def main():
     if backend == "nccl":
         parts = [p.cuda() for p in parts]
         dist.all_gather(parts, torch.from_numpy(xs).cuda())
-        xg = torch.cat([p.cpu() for p in parts]).numpy()
+        parts = [p.cpu() for p in parts]
     else:
         dist.all_gather(parts, torch.from_numpy(xs))
-        xg = torch.cat(parts).numpy()
+    xg4 = np.zeros(dims + [12], dtype=np.complex128)
+    for r_, p_ in enumerate(parts):
+        a, b_ = r_ // PZ, r_ % PZ
+        xg4[a * local[0]:(a + 1) * local[0], b_ * local[1]:(b_ + 1) * local[1]] = p_.numpy().reshape(local + [12])
+    xg = xg4.reshape(-1)
     out["solve_own"] = {"iters": int(sts[0]), "ref_iters": int(str_[0]), "res": float(ress),
                         "res_ref_operator": pc.rel(b, R.dw_double(xg)) if False else float(np.linalg.norm(b - R.dw_double(xg)) / np.linalg.norm(b))}
 
@@ -80,24 +89,24 @@ def main():
         Vd, nc = R.info(1, d), R.info(2, d)
         nv = P.shape[1]
         Plex = P.reshape(Vd, nc, nv)[tt]                         # global lexicographic
-        S.set_interpolation(d, loc(Plex.reshape(-1), nc * nv).reshape(-1, nv))
+        S.set_interpolation(d, loc(Plex.reshape(-1), nc * nv, d).reshape(-1, nv))
     hier = {}
     for d in range(1, levels):
         Vd, nc = R.info(1, d), R.info(2, d)
         vv = pc.crandom(rng, Vd * nc, np.complex64)
-        hier["coarse_apply_d%d" % d] = pc.rel(loc(R.coarse_apply(d, vv), nc), S.level_apply(d, loc(vv, nc)))
+        hier["coarse_apply_d%d" % d] = pc.rel(loc(R.coarse_apply(d, vv), nc, d), S.level_apply(d, loc(vv, nc, d)))
     for d in range(levels - 1):
         Vd, nc = R.info(1, d), R.info(2, d)
         Vc, ncc = R.info(1, d + 1), R.info(2, d + 1)
         vf, vc, phi0 = pc.crandom(rng, Vd * nc, np.complex64), pc.crandom(rng, Vc * ncc, np.complex64), pc.crandom(rng, Vd * nc, np.complex64)
-        hier["restrict_d%d" % d] = pc.rel(loc(R.restrict(d, vf), ncc), S.restrict(d, loc(vf, nc)))
-        hier["interpolate_d%d" % d] = pc.rel(loc(R.interpolate(d, vc), nc), S.interpolate(d, loc(vc, ncc)))
-        hier["smoother_d%d" % d] = pc.rel(loc(R.smoother(d, vf, 2, phi0), nc), S.smoother(d, loc(vf, nc), 2, loc(phi0, nc)))
-        hier["vcycle_d%d" % d] = pc.rel(loc(R.vcycle(d, vf), nc), S.vcycle(d, loc(vf, nc)))
+        hier["restrict_d%d" % d] = pc.rel(loc(R.restrict(d, vf), ncc, d + 1), S.restrict(d, loc(vf, nc, d)))
+        hier["interpolate_d%d" % d] = pc.rel(loc(R.interpolate(d, vc), nc, d), S.interpolate(d, loc(vc, ncc, d + 1)))
+        hier["smoother_d%d" % d] = pc.rel(loc(R.smoother(d, vf, 2, phi0), nc, d), S.smoother(d, loc(vf, nc, d), 2, loc(phi0, nc, d)))
+        hier["vcycle_d%d" % d] = pc.rel(loc(R.vcycle(d, vf), nc, d), S.vcycle(d, loc(vf, nc, d)))
     Vl, ncl = R.info(1, levels - 1), R.info(2, levels - 1)
     vv = pc.crandom(rng, Vl * ncl, np.complex64)
     xr_c, itr = R.coarsest_solve(vv)
-    hier["coarsest_solve"] = pc.rel(loc(xr_c, ncl), S.coarsest_solve(loc(vv, ncl)))
+    hier["coarsest_solve"] = pc.rel(loc(xr_c, ncl, levels - 1), S.coarsest_solve(loc(vv, ncl, levels - 1)))
     hier["coarsest_iters"] = [int(itr), int(S.stat(STAT.COARSE_ITER))]
     w = pc.crandom(rng, R.V * 12)
     hier["preconditioner"] = pc.rel(loc(R.preconditioner(w), 12), S.preconditioner(loc(w, 12)))

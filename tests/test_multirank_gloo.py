@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def run_ranks(lib, backend, levels, tmp_path, world=2, timeout=900):
+def run_ranks(lib, backend, levels, tmp_path, world=2, timeout=900, grid=None):
     port = _free_port()
     procs, outs = [], []
     for r in range(world):
@@ -30,7 +30,8 @@ def run_ranks(lib, backend, levels, tmp_path, world=2, timeout=900):
                    MASTER_PORT=str(port), OMP_NUM_THREADS=str(max(1, (os.cpu_count() or 4) // world)))
         o = str(tmp_path / ("rank%d.json" % r))
         outs.append(o)
-        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "multirank_worker.py"), lib, backend, o, str(levels)],
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "multirank_worker.py"), lib, backend, o, str(levels)]
+                                      + ([grid] if grid else []),
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     logs = []
     for p in procs:
@@ -65,3 +66,13 @@ def test_two_ranks_split_T(emu_lib, oracle_ref, tmp_path, levels):
 def test_four_ranks_split_T(emu_lib, oracle_ref, tmp_path):
     """Four ranks: the +T and -T neighbours of a rank are different processes (with two ranks they coincide)."""
     check(run_ranks(emu_lib, "gloo", 2, tmp_path, world=4), imported_tol_iters=1)
+
+
+def test_two_ranks_split_Z(emu_lib, oracle_ref, tmp_path):
+    """Partition along Z only (process grid 1 x 2)."""
+    check(run_ranks(emu_lib, "gloo", 2, tmp_path, world=2, grid="1,2"))
+
+
+def test_four_ranks_split_T_and_Z(emu_lib, oracle_ref, tmp_path):
+    """Process grid 2 x 2 in T x Z: the clover term needs the corner sites x +- T +- Z of the extended ghost slabs."""
+    check(run_ranks(emu_lib, "gloo", 2, tmp_path, world=4, grid="2,2"))
