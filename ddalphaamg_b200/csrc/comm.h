@@ -3,7 +3,7 @@
 // Reference counterparts: cart_define / neighbor_define (ghost.c:24-66), ghost_sendrecv / ghost_update
 // (ghost_generic.c:171-414: MPI_Isend/Irecv halos), MPI_Allreduce in global_inner_product / global_norm
 // (linalg_generic.c:57,201).  Here: ncclSend/ncclRecv pairs and ncclAllReduce on the library's compute stream
-// (NVLink 5 / NVSwitch); the lattice is partitioned along T (direction 0).  The host-emulation build (tests only)
+// (NVLink 5 / NVSwitch).  The host-emulation build (tests only)
 // routes the same calls through callbacks that the test harness implements with torch.distributed/gloo.
 #pragma once
 #include "common.cuh"

@@ -65,7 +65,7 @@ void dda_upload_source(const double *in_lex);
 double dda_solve_device(double tol, int *status, double *ms_out);
 void dda_download_solution(double *out_lex);
 
-/* ---- multi-GPU: one process per GPU, lattice partitioned along T ("d0 local lattice" != "d0 global lattice").
+/* ---- multi-GPU: one process per GPU, process grid = "d0 global lattice" / "d0 local lattice" (T, Z, ... partitions).
  * Replaces the reference's MPI_COMM_WORLD / MPI_Cart_create plumbing (ghost.c:42-66); call before dd_alpha_amg_init.
  * rank 0 creates the NCCL unique id (dda_comm_unique_id, <= 128 bytes), the launcher broadcasts it (MPI_Bcast,
  * torch.distributed, a file ...) and every rank calls dda_comm_init(rank, size, id, cuda device or -1). */
