@@ -108,6 +108,10 @@ def load_library(path=None):
         raise RuntimeError("%s not found: build the CUDA library with `python -m ddalphaamg_b200.build` "
                            "(there is no CPU fallback)" % path)
     L = C.CDLL(path, mode=C.RTLD_LOCAL)
+    L.dda_is_emulation.restype = C.c_int
+    if L.dda_is_emulation() and os.path.basename(os.path.dirname(os.path.abspath(path))) != "_emu":
+        # the g++ host-emulation build of the host logic is test infrastructure (tests/_emu); it is never a product path
+        raise RuntimeError("%s is a host-emulation test build; the product library is %s" % (path, library_path()))
     dp, fp, ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int)
     L.dd_alpha_amg_init.argtypes = [Par]
     L.dd_alpha_amg_init_external_threading.argtypes = [Par, C.c_int, C.c_int]
