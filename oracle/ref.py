@@ -127,8 +127,11 @@ class Reference:
         self.V = int(np.prod(lattice))
         self._tmp = tempfile.NamedTemporaryFile(suffix=".ini", delete=False)
         self._tmp.close()
+        bc = ini_kw.pop("bc", None)
         write_ini(self._tmp.name, lattice, block, m0=m0, csw=csw, **ini_kw)
-        self.L.ref_init(self._tmp.name.encode(), m0, csw, 2 if ini_kw.get("anti_pbc", 1) else 1, print_mode)
+        if bc is None:
+            bc = 2 if ini_kw.get("anti_pbc", 1) else 1
+        self.L.ref_init(self._tmp.name.encode(), m0, csw, bc, print_mode)
 
     def set_conf(self, U):
         U = np.ascontiguousarray(U, dtype=np.float64)
