@@ -42,7 +42,7 @@ void solver_alloc_fine(Solver &s) {
   solver_process_grid(s, 0, g);
   long V = (long)g.L[0] * g.L[1] * g.L[2] * g.L[3];
   g.sh = (V % 32 == 0) ? 5 : 0;
-  g.block_eo = (p.num_levels > 1);
+  g.block_eo = (p.num_levels > 1) && p.odd_even;   // reference: block_solve_oddeven only with "odd even preconditioning: 1" (schwarz_generic.c:1269-1273)
   g.global_eo = false;
   g.build();
   const long VA = V + g.Vg;     // local + ghost sites (links and vectors carry ghost slabs)

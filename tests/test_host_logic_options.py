@@ -1,0 +1,41 @@
+"""Solver options of the reference's parameter file against the reference itself (host logic, emulation build): plain
+V-cycle instead of the K-cycle, no odd-even preconditioning on the coarsest level, other smoother settings.  The
+reference's interpolation is imported, so the solves must agree iteration by iteration.  One live reference instance at
+a time (created and freed inside each case)."""
+import numpy as np
+import pytest
+
+from conftest import CONF8
+from ddalphaamg_b200 import DDalphaAMG, read_conf
+import parity_common as pc
+
+CASES = {
+    "vcycle_3level": dict(levels=3, block=[2, 2, 2, 2], kw=dict(test_vectors=(12, 16), setup_iter=(1, 1), restart=30, coarse_block=[2, 2, 2, 2], kcycle=0)),
+    "no_odd_even_2level": dict(levels=2, block=[4, 4, 4, 4], kw=dict(test_vectors=(12,), setup_iter=(1,), restart=30, odd_even=0)),
+    "smoother_settings_2level": dict(levels=2, block=[4, 4, 4, 4], kw=dict(test_vectors=(12,), setup_iter=(1,), restart=30, post_smooth=(3,), block_iter=(2,))),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_solver_option_vs_reference(oracle_ref, emu_lib, name):
+    case = CASES[name]
+    dims, plaq, U = read_conf(CONF8)
+    kw = dict(levels=case["levels"], **case["kw"])
+    R = oracle_ref.Reference(dims, case["block"], **kw)
+    S = DDalphaAMG(dims, case["block"], lib=emu_lib, **kw)
+    try:
+        R.set_conf(U)
+        R.setup(1)
+        S.set_conf(U)
+        S.setup(0)
+        out = pc.check_hierarchy(R, S, case["levels"])
+        pc.assert_hierarchy(out)
+        b = np.ones(S.V * 12, dtype=np.complex128)
+        xr, resr, str_ = R.solve(b)
+        xs, ress, sts = S.solve(b)
+        assert sts[0] > 0 and ress < 1e-10
+        assert abs(int(sts[0]) - int(str_[0])) <= 1
+        assert pc.rel(b, R.dw_double(xs)) < 1.5e-10
+    finally:
+        S.free()
+        R.free()
