@@ -74,7 +74,7 @@ def _ip(a):
 def write_ini(path, lattice, block, levels=2, test_vectors=(20, 28), setup_iter=(4, 3), post_smooth=(2, 2),
               block_iter=(4, 4), m0=-0.5, csw=1.0, tol=1e-10, restart=50, max_restart=20, coarse_tol=5e-2,
               coarse_iter=100, coarse_restart=5, mixed_precision=1, anti_pbc=1, method=2, kcycle=1,
-              coarse_lattice=None, coarse_block=None, nthreads=1, local_lattice=None, odd_even=1):
+              coarse_lattice=None, coarse_block=None, nthreads=1, local_lattice=None, odd_even=1, ncycle=(1, 1), relax=(1.0, 1.0)):
     """Writes a .ini in the reference's key:value format (keys: src/init.c:592-962)."""
     loc = local_lattice or lattice
     lines = ["configuration: none", "format: 0", "right hand side: 0",
@@ -86,7 +86,9 @@ def write_ini(path, lattice, block, levels=2, test_vectors=(20, 28), setup_iter=
         lines += ["d%d post smooth iter: %d" % (d, post_smooth[min(d, len(post_smooth) - 1)]),
                   "d%d block iter: %d" % (d, block_iter[min(d, len(block_iter) - 1)]),
                   "d%d test vectors: %d" % (d, test_vectors[min(d, len(test_vectors) - 1)]),
-                  "d%d setup iter: %d" % (d, setup_iter[min(d, len(setup_iter) - 1)])]
+                  "d%d setup iter: %d" % (d, setup_iter[min(d, len(setup_iter) - 1)]),
+                  "d%d preconditioner cycles: %d" % (d, ncycle[min(d, len(ncycle) - 1)]),
+                  "d%d relaxation factor: %.16g" % (d, relax[min(d, len(relax) - 1)])]
     if levels > 2:
         cl = coarse_lattice or [a // b for a, b in zip(lattice, block)]
         lines += ["d1 global lattice: %d %d %d %d" % tuple(cl), "d1 local lattice: %d %d %d %d" % tuple(cl)]

@@ -13,6 +13,7 @@ CASES = {
     "vcycle_3level": dict(levels=3, block=[2, 2, 2, 2], kw=dict(test_vectors=(12, 16), setup_iter=(1, 1), restart=30, coarse_block=[2, 2, 2, 2], kcycle=0)),
     "no_odd_even_2level": dict(levels=2, block=[4, 4, 4, 4], kw=dict(test_vectors=(12,), setup_iter=(1,), restart=30, odd_even=0)),
     "smoother_settings_2level": dict(levels=2, block=[4, 4, 4, 4], kw=dict(test_vectors=(12,), setup_iter=(1,), restart=30, post_smooth=(3,), block_iter=(2,))),
+    "two_cycles_relaxed_2level": dict(levels=2, block=[4, 4, 4, 4], kw=dict(test_vectors=(12,), setup_iter=(1,), restart=30, ncycle=(2,), relax=(0.9,))),
 }
 
 
