@@ -18,7 +18,8 @@
 // between the halves are a per-thread +-1 factor), halves recombined with 6 warp shuffles per operator.  This gives
 // 8 warps per block visit and 16 warps per SM at <= 128 registers (the one-thread-per-site-pair variant ran at 7
 // warps/SM and 21 % issue utilisation, see profiles/).  Clover blocks (even sites) and their inverses (odd sites) are
-// streamed from L2.  MR inner products: warp shuffle + one shared-memory stage.  98.6 KB shared memory -> 2 CTAs/SM.
+// streamed from L2.  MR inner products: warp shuffle + one shared-memory stage.  Shared memory: links 73.7 KB + exchange
+// buffer 24.6 KB + parked r_o 12.3 KB = 110.9 KB -> 2 CTAs/SM.
 #include "solver.h"
 #include "fine_op.cuh"
 #include "halo.h"
