@@ -33,7 +33,7 @@ template <class T> void vsub(cx<T> *z, const cx<T> *x, const cx<T> *y, long n) {
 template <class T> void vadd(cx<T> *z, const cx<T> *x, const cx<T> *y, long n) { launch_n(n, DLAMBDA(long i) { z[i] = x[i] + y[i]; }); }
 template <class T, class S> void vcast(cx<T> *y, const cx<S> *x, long n) { launch_n(n, DLAMBDA(long i) { y[i] = cx<T>((T)x[i].re, (T)x[i].im); }); }
 
-template <class T> void vmulti_axpy(cx<T> *y, cx<T> *const *V, const cd *coef, int m, int sign, long n) {
+template <class T> static void vmulti_axpy_chunk(cx<T> *y, cx<T> *const *V, const cd *coef, int m, int sign, long n) {
   DDA_ASSERT(m <= MAXV);
   if (m <= 0) return;
   PtrArr<T> pa; CoefArr ca;
@@ -82,7 +82,7 @@ template <class T, int KB> __global__ void __launch_bounds__(256) k_multi_dot(Pt
 }
 #endif
 
-template <class T> void vmulti_dot(cd *out, cx<T> *const *V, int m, const cx<T> *w, long n) {
+template <class T> static void vmulti_dot_chunk(cd *out, cx<T> *const *V, int m, const cx<T> *w, long n) {
   DDA_ASSERT(m <= MAXV);
   if (m <= 0) return;
   PtrArr<T> pa;
@@ -112,7 +112,7 @@ template <class T> void vmulti_dot(cd *out, cx<T> *const *V, int m, const cx<T> 
 
 // y += sign * sum_k coef[k] V[k] and ||y_new||^2 in the same pass (the Arnoldi orthogonalisation followed by the norm of
 // the new direction, linsolve_generic.c:859-880: one read of y less than saxpy + norm)
-template <class T> double vmulti_axpy_norm2(cx<T> *y, cx<T> *const *V, const cd *coef, int m, int sign, long n) {
+template <class T> static double vmulti_axpy_norm2_chunk(cx<T> *y, cx<T> *const *V, const cd *coef, int m, int sign, long n) {
   DDA_ASSERT(m <= MAXV);
   PtrArr<T> pa; CoefArr ca;
   for (int k = 0; k < m; k++) { pa.p[k] = V[k]; ca.re[k] = sign * coef[k].re; ca.im[k] = sign * coef[k].im; }
@@ -128,6 +128,21 @@ template <class T> double vmulti_axpy_norm2(cx<T> *y, cx<T> *const *V, const cd 
   double h; d2h(&h, buf, sizeof(double));
   return h;
 }
+
+// public entry points: any number of basis vectors (the coarsest-level GMRES runs up to `coarse grid iterations`, 100 in
+// sample.ini, Arnoldi steps per restart), processed in chunks of MAXV kernel-argument slots
+template <class T> void vmulti_axpy(cx<T> *y, cx<T> *const *V, const cd *coef, int m, int sign, long n) {
+  for (int k0 = 0; k0 < m; k0 += MAXV) vmulti_axpy_chunk(y, V + k0, coef + k0, std::min(MAXV, m - k0), sign, n);
+}
+template <class T> void vmulti_dot(cd *out, cx<T> *const *V, int m, const cx<T> *w, long n) {
+  for (int k0 = 0; k0 < m; k0 += MAXV) vmulti_dot_chunk(out + k0, V + k0, std::min(MAXV, m - k0), w, n);
+}
+template <class T> double vmulti_axpy_norm2(cx<T> *y, cx<T> *const *V, const cd *coef, int m, int sign, long n) {
+  int k0 = 0;
+  for (; m - k0 > MAXV; k0 += MAXV) vmulti_axpy_chunk(y, V + k0, coef + k0, MAXV, sign, n);
+  return vmulti_axpy_norm2_chunk(y, V + k0, coef + k0, m - k0, sign, n);
+}
+
 
 template <class T> void vmulti_dot_norm(cd *out, cx<T> *const *V, int m, const cx<T> *w, long n) {
   DDA_ASSERT(m + 1 <= MAXV);
