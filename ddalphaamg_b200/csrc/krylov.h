@@ -14,6 +14,10 @@ template <class T> struct Fgmres {
   int m = 0, max_restart = 0;
   double tol = 0;
   bool flexible = false, allocated = false;
+  // opt-in (env DDA_SINGLE_REDUCTION=1, coarse-level solvers only): one fused reduction per Arnoldi step, the norm of the
+  // new direction from ||w||^2 - sum |h_i|^2 like the reference's SINGLE_ALLREDUCE_ARNOLDI variant
+  // (linsolve_generic.c:773-805); falls back to an explicit norm when the subtraction cancels
+  bool single_reduction = false;
   std::vector<C *> V, Z;
   C *w = nullptr, *r = nullptr;
   std::vector<cd> H, gamma, c, s, y;   // H column-major: H[j*(m+1)+i]
@@ -61,9 +65,19 @@ template <class T> struct Fgmres {
         if (prec) { prec(Z[j], V[j]); zj = Z[j]; }
         op(w, zj);
         std::vector<cd> hcol(j + 2);
-        vmulti_dot(hcol.data(), V.data(), j + 1, w, n);
+        double hn;
+        if (single_reduction && j + 2 < 64) {
+          vmulti_dot_norm(hcol.data(), V.data(), j + 1, w, n);          // hcol[j+1] = <w,w>
+          const double ww = hcol[j + 1].re;
+          double hh = 0;
+          for (int i = 0; i <= j; i++) hh += norm2(hcol[i]);
+          vmulti_axpy(w, V.data(), hcol.data(), j + 1, -1, n);
+          hn = (ww - hh > 1e-4 * ww) ? std::sqrt(ww - hh) : std::sqrt(vnorm2(w, n));
+        } else {
+          vmulti_dot(hcol.data(), V.data(), j + 1, w, n);
+          hn = std::sqrt(vmulti_axpy_norm2(w, V.data(), hcol.data(), j + 1, -1, n));
+        }
         for (int i = 0; i <= j; i++) h(i, j) = hcol[i];
-        double hn = std::sqrt(vmulti_axpy_norm2(w, V.data(), hcol.data(), j + 1, -1, n));
         h(j + 1, j) = cd(hn, 0);
         if (hn > 1e-15) vscale(V[j + 1], w, 1.0 / hn, n);
         if (hn > tol / 10) {

@@ -76,12 +76,14 @@ void mg_alloc(Solver &s) {
     if (d > 0 && !L.last) {
       L.kc.alloc(L.geo.vlen(), p.kcycle_restart, p.kcycle_max_restart, p.kcycle_tol, true, n);
       Solver *sp = &s; int dd = d;
+      { const char *e = getenv("DDA_SINGLE_REDUCTION"); L.kc.single_reduction = e && atoi(e) != 0; }
       L.kc.op = [sp, dd](cf *out, const cf *in) { mg_apply_op(*sp, dd, out, in); };
       L.kc.prec = [sp, dd](cf *out, const cf *in) { mg_vcycle(*sp, dd, out, in, true); };
     } else if (d > 0 && L.last) {
       long nn = p.odd_even ? L.geo.n_even * L.geo.nc : L.geo.vlen();
       L.kc.alloc(nn, p.coarse_iter, p.coarse_restart, p.coarse_tol, false, n);
       Solver *sp = &s; int dd = d;
+      { const char *e = getenv("DDA_SINGLE_REDUCTION"); L.kc.single_reduction = e && atoi(e) != 0; }
       if (p.odd_even) L.kc.op = [sp](cf *out, const cf *in) { mg_coarsest_schur(*sp, out, in); };
       else L.kc.op = [sp, dd](cf *out, const cf *in) { mg_apply_op(*sp, dd, out, in); };
     }
