@@ -128,7 +128,8 @@ double dd_alpha_amg_set_conf(double *gauge_field) {
   long j = 0; int ifail = 0;
   const int Tg = s.p.global_lattice[0][0];
   for (int t = 0; t < L[0]; t++) {
-    int tg = A->global_time ? A->global_time(t) : t;
+    // without a callback the global time follows from the rank's process coordinate (the reference requires the callback)
+    int tg = A->global_time ? A->global_time(t) : s.lev[0].geo.pc[0] * L[0] + t;
     for (int z = 0; z < L[1]; z++) for (int y = 0; y < L[2]; y++) for (int x = 0; x < L[3]; x++)
       for (int mu = 0; mu < 4; mu++) {
         long i = A->conf_index_fct ? (long)A->conf_index_fct(t, z, y, x, mu) : 18 * (4 * lexsite(L, t, z, y, x) + mu);
@@ -150,6 +151,7 @@ double dd_alpha_amg_set_conf(double *gauge_field) {
     vscale(L0.Dd, L0.Dd, 0.5, V * 36);
     halo_exchange<cd>(L0.geo, L0.Dd, 36, L0.geo.sh);
     solver_refresh_float_op(s);
+    if (!s.h_gauge.empty()) solver_sync_host_mirrors(s, false);
   } else {
     solver_upload_conf(s, h.data());
   }

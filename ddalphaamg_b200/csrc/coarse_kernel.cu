@@ -48,6 +48,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// acc += m * v  /  acc += conj(m) * v  on split real/imaginary accumulators: 4 FFMA each (written with explicit fma, the
+// compiler may not re-associate `a += b*c - d*e` into two fused operations)
+__device__ __forceinline__ void cmac(float &ar, float &ai, float mx, float my, float vx, float vy) {
+  ar = __fmaf_rn(-my, vy, __fmaf_rn(mx, vx, ar)); ai = __fmaf_rn(my, vx, __fmaf_rn(mx, vy, ai));
+}
+__device__ __forceinline__ void cmacc(float &ar, float &ai, float mx, float my, float vx, float vy) {
+  ar = __fmaf_rn(my, vy, __fmaf_rn(mx, vx, ar)); ai = __fmaf_rn(-my, vx, __fmaf_rn(mx, vy, ai));
+}
+
 // Register tiling: thread t of the 128 owns the component PAIR p = t % (n/2) of group g = t / (n/2)  (G groups, G | n/2
 // chosen by the host, threads beyond G*n/2 idle).  Forward product: rows 2p, 2p+1 times the group's chunk of n/G
 // columns; daggered product: columns 2p, 2p+1 times the group's chunk of rows.  Both walk the column-major block with
@@ -134,10 +143,10 @@ k_coarse_full(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
             const float4 v = v4[cc >> 1];
             const float4 m0 = *reinterpret_cast<const float4 *>(Mb + (size_t)cc * n);
             const float4 m1 = *reinterpret_cast<const float4 *>(Mb + (size_t)(cc + 1) * n);
-            f0r += m0.x * v.x - m0.y * v.y; f0i += m0.x * v.y + m0.y * v.x;
-            f1r += m0.z * v.x - m0.w * v.y; f1i += m0.z * v.y + m0.w * v.x;
-            f0r += m1.x * v.z - m1.y * v.w; f0i += m1.x * v.w + m1.y * v.z;
-            f1r += m1.z * v.z - m1.w * v.w; f1i += m1.z * v.w + m1.w * v.z;
+            cmac(f0r, f0i, m0.x, m0.y, v.x, v.y);
+            cmac(f1r, f1i, m0.z, m0.w, v.x, v.y);
+            cmac(f0r, f0i, m1.x, m1.y, v.z, v.w);
+            cmac(f1r, f1i, m1.z, m1.w, v.z, v.w);
           }
         }
         if (m > 0) {                      // daggered: conj(M[r][c]) w[r]
@@ -150,10 +159,10 @@ k_coarse_full(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
             const float4 wv = *reinterpret_cast<const float4 *>(w + 2 * ip);
             const float4 m0 = *reinterpret_cast<const float4 *>(M0 + 2 * ip);
             const float4 m1 = *reinterpret_cast<const float4 *>(M1 + 2 * ip);
-            a0r += m0.x * wv.x + m0.y * wv.y; a0i += m0.x * wv.y - m0.y * wv.x;
-            a0r += m0.z * wv.z + m0.w * wv.w; a0i += m0.z * wv.w - m0.w * wv.z;
-            a1r += m1.x * wv.x + m1.y * wv.y; a1i += m1.x * wv.y - m1.y * wv.x;
-            a1r += m1.z * wv.z + m1.w * wv.w; a1i += m1.z * wv.w - m1.w * wv.z;
+            cmacc(a0r, a0i, m0.x, m0.y, wv.x, wv.y);
+            cmacc(a0r, a0i, m0.z, m0.w, wv.z, wv.w);
+            cmacc(a1r, a1i, m1.x, m1.y, wv.x, wv.y);
+            cmacc(a1r, a1i, m1.z, m1.w, wv.z, wv.w);
             ip++; if (ip == P) ip = 0;
           }
           zr[m - 1][0] = a0r; zi[m - 1][0] = a0i; zr[m - 1][1] = a1r; zi[m - 1][1] = a1i;
@@ -286,10 +295,10 @@ k_coarse_sap_mr(CoarseOp op, cf *__restrict__ x, const cf *__restrict__ rin, con
             const float4 v = v4[cc >> 1];
             const float4 m0 = *reinterpret_cast<const float4 *>(Mb + (size_t)cc * n);
             const float4 m1 = *reinterpret_cast<const float4 *>(Mb + (size_t)(cc + 1) * n);
-            f0r += m0.x * v.x - m0.y * v.y; f0i += m0.x * v.y + m0.y * v.x;
-            f1r += m0.z * v.x - m0.w * v.y; f1i += m0.z * v.y + m0.w * v.x;
-            f0r += m1.x * v.z - m1.y * v.w; f0i += m1.x * v.w + m1.y * v.z;
-            f1r += m1.z * v.z - m1.w * v.w; f1i += m1.z * v.w + m1.w * v.z;
+            cmac(f0r, f0i, m0.x, m0.y, v.x, v.y);
+            cmac(f1r, f1i, m0.z, m0.w, v.x, v.y);
+            cmac(f0r, f0i, m1.x, m1.y, v.z, v.w);
+            cmac(f1r, f1i, m1.z, m1.w, v.z, v.w);
           }
           float *d = reinterpret_cast<float *>(Dr + jb.i * n + 2 * p);
           atomicAdd(d, f0r); atomicAdd(d + 1, f0i); atomicAdd(d + 2, f1r); atomicAdd(d + 3, f1i);
@@ -304,10 +313,10 @@ k_coarse_sap_mr(CoarseOp op, cf *__restrict__ x, const cf *__restrict__ rin, con
             const float4 wv = *reinterpret_cast<const float4 *>(wv_ + 2 * ip);
             const float4 m0 = *reinterpret_cast<const float4 *>(M0 + 2 * ip);
             const float4 m1 = *reinterpret_cast<const float4 *>(M1 + 2 * ip);
-            a0r += m0.x * wv.x + m0.y * wv.y; a0i += m0.x * wv.y - m0.y * wv.x;
-            a0r += m0.z * wv.z + m0.w * wv.w; a0i += m0.z * wv.w - m0.w * wv.z;
-            a1r += m1.x * wv.x + m1.y * wv.y; a1i += m1.x * wv.y - m1.y * wv.x;
-            a1r += m1.z * wv.z + m1.w * wv.w; a1i += m1.z * wv.w - m1.w * wv.z;
+            cmacc(a0r, a0i, m0.x, m0.y, wv.x, wv.y);
+            cmacc(a0r, a0i, m0.z, m0.w, wv.z, wv.w);
+            cmacc(a1r, a1i, m1.x, m1.y, wv.x, wv.y);
+            cmacc(a1r, a1i, m1.z, m1.w, wv.z, wv.w);
             ip++; if (ip == P) ip = 0;
           }
           float *d = reinterpret_cast<float *>(Dr + jb.j * n + 2 * p);

@@ -26,14 +26,15 @@ static ncclComm_t g_nccl = nullptr;
   fprintf(stderr, "NCCL error %s: %s\n", #x, ncclGetErrorString(r_)); ::dda::fatal("nccl", __FILE__, __LINE__); } } while (0)
 
 void comm_sendrecv(const void *send, void *recv, size_t bytes, int to, int from) {
+  if (to == g_comm.rank && from == g_comm.rank) { d2d(recv, send, bytes); return; }   // own periodic neighbour
   DDA_ASSERT(g_nccl);
   NCCL_CHECK(ncclGroupStart());
   NCCL_CHECK(ncclSend(send, bytes, ncclChar, to, g_nccl, g_stream));
   NCCL_CHECK(ncclRecv(recv, bytes, ncclChar, from, g_nccl, g_stream));
   NCCL_CHECK(ncclGroupEnd());
 }
-void comm_group_begin() { NCCL_CHECK(ncclGroupStart()); }
-void comm_group_end() { NCCL_CHECK(ncclGroupEnd()); }
+void comm_group_begin() { if (g_nccl) NCCL_CHECK(ncclGroupStart()); }
+void comm_group_end() { if (g_nccl) NCCL_CHECK(ncclGroupEnd()); }
 void comm_allreduce_sum(double *buf, int n) {
   if (!g_comm.active()) return;
   NCCL_CHECK(ncclAllReduce(buf, buf, n, ncclDouble, ncclSum, g_nccl, g_stream));
@@ -47,6 +48,7 @@ void comm_finalize() {
 static dda_sendrecv_fn g_cb_sendrecv = nullptr;
 static dda_allreduce_fn g_cb_allreduce = nullptr;
 void comm_sendrecv(const void *send, void *recv, size_t bytes, int to, int from) {
+  if (to == g_comm.rank && from == g_comm.rank) { d2d(recv, send, bytes); return; }   // own periodic neighbour
   DDA_ASSERT(g_cb_sendrecv);
   g_cb_sendrecv(send, recv, (long)bytes, to, from);
 }

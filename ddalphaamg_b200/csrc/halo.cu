@@ -10,7 +10,7 @@ template <class E> void halo_exchange(const Geometry &g, E *v, int nc, int sh) {
   if (!g.partitioned()) return;
   const Lay lay = {nc, sh};
   for (int m = 0; m < 4; m++) {
-    if (g.P[m] <= 1) continue;
+    if (!g.split(m)) continue;
     const long ns = g.slab[m];
     const size_t bytes = sizeof(E) * (size_t)ns * nc;
     E *b0 = (E *)comm_buffer(0, bytes), *b1 = (E *)comm_buffer(1, bytes);

@@ -87,7 +87,7 @@ void Geometry::build() {
   int lo[4] = {0, 0, 0, 0}, hi[4] = {L[0] - 1, L[1] - 1, L[2] - 1, L[3] - 1};
   for (int m = 0; m < 4; m++) {
     slab[m] = 0; gh_off[m] = gh_off[4 + m] = -1;
-    if (P[m] <= 1) continue;
+    if (!split(m)) continue;
     for (int side = 0; side < 2; side++) {
       const int d = side == 0 ? m : 4 + m;       // +m ghost <- neighbour's x_m = 0 slice ; -m ghost <- its x_m = L-1 slice
       const int src = side == 0 ? 0 : L[m] - 1, dst = side == 0 ? L[m] : -1;
@@ -122,7 +122,7 @@ void Geometry::build() {
     const int m = d & 3, sgn = d < 4 ? +1 : -1;
     int q[4] = {c[0], c[1], c[2], c[3]};
     q[m] += sgn;
-    if (P[m] <= 1) q[m] = (q[m] + L[m]) % L[m];
+    if (!split(m)) q[m] = (q[m] + L[m]) % L[m];
     else if (q[m] < -1 || q[m] > L[m]) return -1;
     return ext[eidx(q)];
   };

@@ -36,6 +36,11 @@ struct Geometry {
   // direction spans the lattice extended by the slabs of the earlier ones (corner sites for the clover term).
   // Reference: ghost shell of data_layout.c:24-40, ghost_generic.c.
   int P[4] = {1, 1, 1, 1}, pc[4] = {0, 0, 0, 0};
+  // fg[mu] != 0: direction mu carries ghost slabs although the process grid has extent 1 there -- the rank is its own
+  // periodic neighbour (slabs filled by a local copy).  Runs every partitioned code path (interior / boundary kernels,
+  // pack kernel, ghost branches) on ONE GPU; set by DDA_FORCE_SPLIT for the parity tests of those paths.
+  int fg[4] = {0, 0, 0, 0};
+  bool split(int m) const { return P[m] > 1 || fg[m] != 0; }
   long Vg = 0;
   long gh_off[8] = {-1, -1, -1, -1, -1, -1, -1, -1};   // first site index (>= V) of slab d (d<4: +mu, d>=4: -mu)
   long slab[4] = {0, 0, 0, 0};

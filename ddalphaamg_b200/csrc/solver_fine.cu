@@ -23,6 +23,11 @@ void solver_process_grid(Solver &s, int depth, Geometry &g) {
   for (int m = 0; m < 4; m++) DDA_ASSERT(g.P[m] == p.global_lattice[0][m] / p.local_lattice[0][m]);
   int r = g_comm.rank;
   for (int m = 3; m >= 0; m--) { g.pc[m] = r % g.P[m]; r /= g.P[m]; }
+  // DDA_FORCE_SPLIT=<letters of TZYX>: ghost slabs in these directions even where the process grid has extent 1
+  if (const char *e = getenv("DDA_FORCE_SPLIT")) {
+    const char *names = "TZYX";
+    for (int m = 0; m < 4; m++) g.fg[m] = (strchr(e, names[m]) || strchr(e, names[m] + 32)) ? 1 : 0;
+  }
 }
 
 void solver_alloc_fine(Solver &s) {
@@ -76,6 +81,9 @@ void solver_upload_conf(Solver &s, const double *gauge_lex) {
   s.m0_op = s.p.m0;
   solver_refresh_float_op(s);
   s.conf_set = true;
+  // pointers handed out by dd_alpha_amg_get_gauge_pointer / get_clover_pointer stay live and current, like the
+  // reference's pointers into op_double (dirac.c:171-176)
+  if (!s.h_gauge.empty()) solver_sync_host_mirrors(s, false);
 }
 
 void solver_refresh_float_op(Solver &s) {
@@ -134,6 +142,7 @@ void solver_shift_mass(Solver &s, double new_m0) {
     }
   }
   s.m0_op = new_m0;
+  if (!s.h_gauge.empty()) solver_sync_host_mirrors(s, false);   // the clover mirror follows the shifted diagonal
 }
 
 

@@ -37,8 +37,8 @@ k_restrict_fine(Transfer t, cf *__restrict__ out, long site_stride, long offset,
           for (int c = 0; c < 12; c++) {
             const float2 p = __ldg(reinterpret_cast<const float2 *>(P + base + ((long)c << 5)));
             const int ch = c / 6;
-            ar[ch][k] += p.x * v[c].re + p.y * v[c].im;       // conj(P) * phi
-            ai[ch][k] += p.x * v[c].im - p.y * v[c].re;
+            ar[ch][k] = __fmaf_rn(p.y, v[c].im, __fmaf_rn(p.x, v[c].re, ar[ch][k]));       // conj(P) * phi
+            ai[ch][k] = __fmaf_rn(-p.y, v[c].re, __fmaf_rn(p.x, v[c].im, ai[ch][k]));
           }
         }
       }

@@ -27,12 +27,25 @@ def main():
     dist.init_process_group(backend, rank=rank, world_size=world)
     comm_init(lib)
     dims, plaq, U = read_conf(os.path.join(ROOT, "tests", "golden", "conf_8x8x8x8b6.0000id3n1"))
+    mass = {}
+    if len(sys.argv) > 6:
+        # synthetic field on a lattice of its own (argv[6] = "T,Z,Y,X"): lets a rank own interior AND boundary 4^4 blocks
+        from ddalphaamg_b200 import random_gauge_field
+        dims = [int(v) for v in sys.argv[6].split(",")]
+        U = random_gauge_field(dims, seed=77, eps=0.3)
+        plaq = None
+        mass = dict(m0=-0.3, csw=1.0)
     # process grid PT x PZ (argv[5] = "PT,PZ", default: all ranks along T); rank = cT * PZ + cZ (T slowest)
     PT, PZ = (int(v) for v in sys.argv[5].split(",")) if len(sys.argv) > 5 else (world, 1)
     assert PT * PZ == world
     cT, cZ = rank // PZ, rank % PZ
     local = [dims[0] // PT, dims[1] // PZ] + dims[2:]
-    if levels == 2 and (world > 2 or PZ > 1):
+    if len(sys.argv) > 6:
+        block = [4, 4, 4, 4]
+        kw = dict(levels=levels, test_vectors=(20, 28)[:max(1, levels - 1)], setup_iter=(2, 1)[:max(1, levels - 1)], restart=20, **mass)
+        if levels > 2:
+            kw["coarse_block"] = [2, 2, 2, 2]
+    elif levels == 2 and (world > 2 or PZ > 1):
         block = [2, 2, 2, 2]      # local T extent 8 / world = 2: one block in T per rank, coarse local T extent 1
         kw = dict(levels=2, test_vectors=(12,), setup_iter=(2,), restart=20)
     elif levels == 2:
@@ -43,14 +56,14 @@ def main():
         kw = dict(levels=3, test_vectors=(20, 28), setup_iter=(1, 1), restart=50, coarse_block=[2, 2, 2, 2])
     out = {"rank": rank}
     R = ref.Reference(dims, block, **kw)
-    R.set_conf(U)
-    R.setup(kw["setup_iter"][0])
+    plaq_ref = R.set_conf(U)
+    R.setup(kw["setup_iter"][0], nthreads=max(1, (os.cpu_count() or 1) // world) if len(sys.argv) > 6 else 1)
     S = DDalphaAMG(dims, block, lib=lib, local_lattice=local, **kw)
     def part(a4, c_t, c_z):    # this (or another) rank's part of an array whose first four axes are the global T,Z,Y,X
         lt, lz = a4.shape[0] // PT, a4.shape[1] // PZ
         return np.ascontiguousarray(a4[c_t * lt:(c_t + 1) * lt, c_z * lz:(c_z + 1) * lz])
 
-    out["plaq_err"] = abs(S.set_conf(part(U, cT, cZ)) - plaq)
+    out["plaq_err"] = abs(S.set_conf(part(U, cT, cZ)) - (plaq if plaq is not None else plaq_ref))
 
     def loc(v, nc, depth=0):     # local part of a global lexicographic vector of level `depth` with nc entries per site
         g = [R.info(7 + m, depth) for m in range(4)]

@@ -22,16 +22,17 @@ def _free_port():
     return p
 
 
-def run_ranks(lib, backend, levels, tmp_path, world=2, timeout=900, grid=None):
+def run_ranks(lib, backend, levels, tmp_path, world=2, timeout=900, grid=None, lattice=None, extra_env=None):
     port = _free_port()
     procs, outs = [], []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
                    MASTER_PORT=str(port), OMP_NUM_THREADS=str(max(1, (os.cpu_count() or 4) // world)))
+        env.update(extra_env or {})
         o = str(tmp_path / ("rank%d.json" % r))
         outs.append(o)
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "multirank_worker.py"), lib, backend, o, str(levels)]
-                                      + ([grid] if grid else []),
+                                      + ([grid or "%d,1" % world] if (grid or lattice) else []) + ([lattice] if lattice else []),
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     logs = []
     for p in procs:
@@ -76,3 +77,10 @@ def test_two_ranks_split_Z(emu_lib, oracle_ref, tmp_path):
 def test_four_ranks_split_T_and_Z(emu_lib, oracle_ref, tmp_path):
     """Process grid 2 x 2 in T x Z: the clover term needs the corner sites x +- T +- Z of the extended ghost slabs."""
     check(run_ranks(emu_lib, "gloo", 2, tmp_path, world=4, grid="2,2"))
+
+
+@pytest.mark.parametrize("dirs,levels", [("T", 2), ("TZ", 3)])
+def test_forced_split_single_rank(emu_lib, oracle_ref, tmp_path, dirs, levels):
+    """DDA_FORCE_SPLIT: ONE rank that carries ghost slabs and is its own periodic neighbour -- the partitioned code paths
+    (pack kernel, ghost neighbour tables, interior / boundary lists, coarse ghost hops) without a second process."""
+    check(run_ranks(emu_lib, "gloo", levels, tmp_path, world=1, extra_env={"DDA_FORCE_SPLIT": dirs}))
