@@ -18,44 +18,13 @@
 // Algorithmic traffic per site: (5 n^2 + 6 n + 4 n) * 8 B  (SURVEY.md section 8d counts (4n^2 + n(n+1)/2 + 2n) * 8 B
 // because the reference stores S packed Hermitian; bench.py reports against the SURVEY figure).
 #include "coarse_op.h"
+#include "tma.cuh"
 #include <cstdint>
 #include <vector>
 
 namespace dda {
 
 #ifndef DDA_HOST_EMU
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-// acc += m * v  /  acc += conj(m) * v  on split real/imaginary accumulators: 4 FFMA each (written with explicit fma, the
-// compiler may not re-associate `a += b*c - d*e` into two fused operations)
-__device__ __forceinline__ void cmac(float &ar, float &ai, float mx, float my, float vx, float vy) {
-  ar = __fmaf_rn(-my, vy, __fmaf_rn(mx, vx, ar)); ai = __fmaf_rn(my, vx, __fmaf_rn(mx, vy, ai));
-}
-__device__ __forceinline__ void cmacc(float &ar, float &ai, float mx, float my, float vx, float vy) {
-  ar = __fmaf_rn(my, vy, __fmaf_rn(mx, vx, ar)); ai = __fmaf_rn(-my, vx, __fmaf_rn(mx, vy, ai));
-}
 
 // Register tiling: thread t of the 128 owns the component PAIR p = t % (n/2) of group g = t / (n/2)  (G groups, G | n/2
 // chosen by the host, threads beyond G*n/2 idle).  Forward product: rows 2p, 2p+1 times the group's chunk of n/G

@@ -41,4 +41,11 @@ bool coarse_apply_fast(const CoarseOp &op, cf *out, const cf *in, cf *Z);
 bool coarse_sap_mr_fast(const CoarseOp &op, cf *x, const cf *r, const int *d_blocklist, int nblk, int bs, int biter,
                         const int *d_jobs, int njobs);
 
+// even-odd Schur complement of the coarsest operator as streaming kernels (sm_100a only; schur_kernel.cu); vectors are
+// full-lattice arrays in global even-odd order, Z: 4*n complex per site, `skip`: device flag (kernels return if set)
+bool schur_fast_supported(const CoarseOp &op);
+void schur_hop(const CoarseOp &op, int phase, const cf *in, const cf *self, cf *dir, cf *Z, const int *skip);
+void schur_mid(const CoarseOp &op, const cf *eta, const cf *dir, const cf *Z, cf *out, float a, float b, float cS, const int *skip);
+void schur_fin(const CoarseOp &op, const cf *eta, const cf *dir, const cf *Z, cf *out, float a, float b, const int *skip);
+
 }  // namespace dda

@@ -23,6 +23,8 @@ void comm_group_begin();
 void comm_group_end();
 // in-place sum over all ranks of n doubles (device buffer in the CUDA build)
 void comm_allreduce_sum(double *buf, int n);
+// recv[r * bytes ...] = send of rank r, for all ranks (device buffers in the CUDA build; ncclAllGather)
+void comm_allgather(const void *send, void *recv, size_t bytes);
 // scratch buffers for packed faces (two, grown on demand)
 void *comm_buffer(int which, size_t bytes);
 void comm_finalize();

@@ -13,13 +13,6 @@
 
 namespace dda {
 
-static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-struct ProfScope {
-  Solver &s; double *acc; double t0;
-  ProfScope(Solver &s_, double *a) : s(s_), acc(a), t0(0) { if (s.profile) { dev_sync(); t0 = now_s(); } }
-  ~ProfScope() { if (s.profile) { dev_sync(); *acc += now_s() - t0; } }
-};
-
 void lv_halo(Level &L, const cf *v) { halo_exchange<cf>(L.geo, const_cast<cf *>(v), L.geo.nc, L.geo.sh); }
 
 void lv_apply(Level &L, cf *out, const cf *in, SiteSel sel, int hop, int dir, int self, int outmode, const cf *eta,
@@ -164,43 +157,6 @@ void mg_smoother(Solver &s, int depth, cf *phi, const cf *eta, int iters, bool z
   }
   double rf = s.p.relax_fac[depth];
   if (rf != 1.0) vscale(phi, phi, rf, n);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// coarsest level: even-odd preconditioned GMRES.  Vectors are in global even-odd order [even sites | odd sites].
-void mg_coarsest_schur(Solver &s, cf *out, const cf *in) {
-  Level &L = s.lev[s.nlev - 1];
-  const Geometry &g = L.geo;
-  long ne = g.n_even, no = g.V - g.n_even;
-  cf *t0 = L.w[0], *t1 = L.w[1];
-  lv_halo(L, in);
-  lv_apply(L, t0, in, sel_range(ne, no), HOP_ALL, 0, SELF_NONE, OUT_SET);                 // t0_o = N_oe in_e
-  lv_apply(L, t1, t0, sel_range(ne, no), HOP_NONE, 0, SELF_CINV, OUT_NEG);                // t1_o = -Soo^-1 t0_o
-  lv_halo(L, t1);
-  lv_apply(L, out, t1, sel_range(0, ne), HOP_ALL, 0, SELF_C, OUT_SET, nullptr, in);       // out_e = See in_e + N_eo t1_o
-}
-
-void mg_coarsest_solve(Solver &s) {
-  Level &L = s.lev[s.nlev - 1];
-  ProfScope ps(s, &s.t_coarse_solve);
-  const Geometry &g = L.geo;
-  long ne = g.n_even, no = g.V - g.n_even;
-  cf *b = L.vb, *x = L.vx, *t1 = L.w[2], *t2 = L.w[3];
-  if (!s.p.odd_even) {
-    int it = L.kc.solve(x, b, true);
-    s.coarse_iter_count += it;
-    return;
-  }
-  // x_o = Soo^-1 b_o ; b_e <- b_e - H_eo x_o          (coarse_solve_odd_even, coarse_oddeven_generic.c:1139-1147)
-  lv_apply(L, x, b, sel_range(ne, no), HOP_NONE, 0, SELF_CINV, OUT_SET);
-  lv_halo(L, x);
-  lv_apply(L, t1, x, sel_range(0, ne), HOP_ALL, 0, SELF_NONE, OUT_ETA_MINUS, b);
-  int it = L.kc.solve(x, t1, true);
-  s.coarse_iter_count += it;
-  // x_o = Soo^-1 (b_o - H_oe x_e)
-  lv_halo(L, x);
-  lv_apply(L, t2, x, sel_range(ne, no), HOP_ALL, 0, SELF_NONE, OUT_ETA_MINUS, b);
-  lv_apply(L, x, t2, sel_range(ne, no), HOP_NONE, 0, SELF_CINV, OUT_SET);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -79,18 +79,13 @@ void mg_alloc(Solver &s) {
       { const char *e = getenv("DDA_SINGLE_REDUCTION"); L.kc.single_reduction = e && atoi(e) != 0; }
       L.kc.op = [sp, dd](cf *out, const cf *in) { mg_apply_op(*sp, dd, out, in); };
       L.kc.prec = [sp, dd](cf *out, const cf *in) { mg_vcycle(*sp, dd, out, in, true); };
-    } else if (d > 0 && L.last) {
-      long nn = p.odd_even ? L.geo.n_even * L.geo.nc : L.geo.vlen();
-      L.kc.alloc(nn, p.coarse_iter, p.coarse_restart, p.coarse_tol, false, n);
-      Solver *sp = &s; int dd = d;
-      { const char *e = getenv("DDA_SINGLE_REDUCTION"); L.kc.single_reduction = e && atoi(e) != 0; }
-      if (p.odd_even) L.kc.op = [sp](cf *out, const cf *in) { mg_coarsest_schur(*sp, out, in); };
-      else L.kc.op = [sp, dd](cf *out, const cf *in) { mg_apply_op(*sp, dd, out, in); };
     }
   }
+  coarsest_alloc(s);     // coarsest-level solver (device-resident GMRES, gathered lattice when the level is partitioned)
 }
 
 void mg_free(Solver &s) {
+  coarsest_free(s);
   for (int d = 0; d < s.nlev; d++) {
     Level &L = s.lev[d];
     for (auto v : L.tv) dev_free(v);
@@ -133,7 +128,7 @@ void mg_rebuild_coarse(Solver &s, int depth) {
     }
   }
   halo_exchange<cf>(N.geo, c.F, 4 * (int)nn, 0);     // forward hops of the -mu ghost sites (used by the backward hop)
-  if (N.last && s.p.odd_even) coarse_invert_odd_self(c);
+  if (N.last) coarsest_refresh(s);
 }
 
 static void define_interpolation(Solver &s, int depth) {

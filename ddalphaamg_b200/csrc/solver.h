@@ -7,6 +7,8 @@
 #include "coarse_op.h"
 #include "transfer.h"
 #include "krylov.h"
+#include "dev_gmres.h"
+#include <chrono>
 
 namespace dda {
 
@@ -36,6 +38,26 @@ struct Level {
   Fgmres<float> kc;                       // K-cycle wrapper (depth >= 1, not last) or coarsest-level solver (last)
 };
 
+// Coarsest-level solver state.  With several ranks (or forced ghost slabs) and a small coarsest lattice, every rank
+// holds a copy of the WHOLE coarsest operator and solves the gathered system redundantly: one all-gather of the
+// right-hand side per solve instead of two halo exchanges and two all-reduces per Arnoldi step on a few hundred sites
+// per rank.  This is the limit case of the reference's coarse-level gathering onto fewer processes
+// (gathering_generic.c:44-194, 285-346: vector_PRECISION_gather / distribute, idle ranks).
+struct Coarsest {
+  bool active = false, replicated = false, fast = false, host_driven = false;
+  Geometry rgeo;                          // replicated: global coarsest lattice, no ghost slabs
+  CoarseOp rop;                           // replicated: operator of the global lattice (own storage)
+  Geometry *geo = nullptr;                // -> rgeo or the last level's geometry
+  CoarseOp *op = nullptr;                 // -> rop or the last level's operator
+  cf *b = nullptr, *x = nullptr;          // right-hand side / solution in `geo` order
+  cf *t[4] = {};                          // work vectors (full lattice + ghosts)
+  cf *dir = nullptr, *Z = nullptr;        // scratch of the scatter-form Schur kernels
+  cf *gbuf = nullptr;                     // all-gather staging of a vector (replicated)
+  int *d_src = nullptr, *d_own = nullptr; // replicated: gather source of global site g; global site of local site k
+  DevGmres dg;                            // device-resident GMRES (default)
+  Fgmres<float> hostk;                    // host-driven GMRES (DDA_COARSEST_HOST=1: round-1 behaviour, for comparison)
+};
+
 struct Solver {
   Params p;
   int nlev = 0;
@@ -43,6 +65,7 @@ struct Solver {
   bool fine_alloc = false, conf_set = false, setup_done = false;
   double plaq = 0.0;
   double m0_op = 0.0;                     // mass currently folded into the clover diagonal
+  Coarsest cst;
   Fgmres<double> outer;                   // outer double-precision FGMRES ("mixed precision: 0/1")
   FgmresMP outer_mp;                      // mixed-precision outer solver ("mixed precision: 2", linsolve.c:153)
   cd *xb = nullptr, *xx = nullptr;        // device source / solution of the outer solve (native layout)
@@ -59,6 +82,14 @@ struct Solver {
 };
 
 extern Solver *g_solver;
+
+// device-synchronising wall-clock timer of one operator class (only when Solver::profile is set)
+inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+struct ProfScope {
+  Solver &s; double *acc; double t0;
+  ProfScope(Solver &s_, double *a) : s(s_), acc(a), t0(0) { if (s.profile) { dev_sync(); t0 = now_s(); } }
+  ~ProfScope() { if (s.profile) { dev_sync(); *acc += now_s() - t0; } }
+};
 
 // ---- fine operator management (solver_fine.cu)
 void solver_process_grid(Solver &s, int depth, Geometry &g);
@@ -80,7 +111,11 @@ void mg_preconditioner(Solver &s, cd *out, const cd *in);     // one V/K-cycle o
 void mg_vcycle(Solver &s, int depth, cf *phi, const cf *eta, bool zero_guess);
 void mg_smoother(Solver &s, int depth, cf *phi, const cf *eta, int iters, bool zero_guess);
 void mg_coarsest_solve(Solver &s);
-void mg_coarsest_schur(Solver &s, cf *out, const cf *in);   // even-site Schur complement of the coarsest operator
+// even-site Schur complement of the coarsest operator (vectors in the coarsest solver's geometry, Coarsest::geo)
+void mg_coarsest_schur(Solver &s, cf *out, const cf *in, const int *skip = nullptr);
+void coarsest_alloc(Solver &s);          // after the levels' geometries exist
+void coarsest_free(Solver &s);
+void coarsest_refresh(Solver &s);        // after the last level's operator changed: gather (if replicated) + Soo^-1
 void mg_apply_op(Solver &s, int depth, cf *out, const cf *in);  // full operator of the level (float)
 double mg_solve(Solver &s, cd *x, const cd *b, double tol, int *status);
 // fills the ghost slabs of a level's float vector (no-op on an unpartitioned level)

@@ -138,7 +138,7 @@ void solver_shift_mass(Solver &s, double new_m0) {
       CoarseOp &c = s.lev[d].cop;
       cf *S = c.S; int n = c.n; float df = (float)delta;
       launch_n(c.V * n, DLAMBDA(long i) { long site = i / n; int r = (int)(i - site * n); S[site * (long)n * n + (long)r * n + r].re += df; });
-      if (s.lev[d].last) coarse_invert_odd_self(c);
+      if (s.lev[d].last) coarsest_refresh(s);
     }
   }
   s.m0_op = new_m0;

@@ -84,3 +84,9 @@ def test_forced_split_single_rank(emu_lib, oracle_ref, tmp_path, dirs, levels):
     """DDA_FORCE_SPLIT: ONE rank that carries ghost slabs and is its own periodic neighbour -- the partitioned code paths
     (pack kernel, ghost neighbour tables, interior / boundary lists, coarse ghost hops) without a second process."""
     check(run_ranks(emu_lib, "gloo", levels, tmp_path, world=1, extra_env={"DDA_FORCE_SPLIT": dirs}))
+
+
+def test_two_ranks_partitioned_coarsest(emu_lib, oracle_ref, tmp_path):
+    """Replication of the coarsest level switched off: the device-resident GMRES runs on the partitioned coarsest lattice
+    (halo exchanges inside the Schur complement, all-reduces on the device-side Hessenberg buffers)."""
+    check(run_ranks(emu_lib, "gloo", 3, tmp_path, extra_env={"DDA_COARSEST_REPLICATE_MAX": "0"}))
