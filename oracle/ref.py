@@ -39,6 +39,8 @@ def load(flavour=""):
     L.ref_setup.argtypes = [C.c_int, ip]
     L.ref_setup_mt.argtypes = [C.c_int, C.c_int, ip]
     L.ref_solve.argtypes = [dp, dp, C.c_double, ip]; L.ref_solve.restype = C.c_double
+    L.ref_solve_scaled.argtypes = [dp, dp, C.c_double, C.c_double, C.c_double, ip]; L.ref_solve_scaled.restype = C.c_double
+    L.ref_shift_mass.argtypes = [C.c_double]
     L.ref_solve_mt.argtypes = [dp, dp, C.c_double, ip, dp]; L.ref_solve_mt.restype = C.c_double
     L.ref_info.argtypes = [C.c_int, C.c_int]; L.ref_info.restype = C.c_int
     L.ref_get_D.argtypes = [dp]; L.ref_get_clover.argtypes = [dp]
@@ -147,12 +149,19 @@ class Reference:
             self.L.ref_setup(iters, _ip(st))
         return st
 
-    def solve(self, b, tol=1e-10):
+    def solve(self, b, tol=1e-10, scale_even=1.0, scale_odd=1.0):
         b = np.ascontiguousarray(b, dtype=np.complex128)
         x = np.zeros_like(b)
         st = np.zeros(2, dtype=np.int32)
-        res = self.L.ref_solve(_dp(x), _dp(b), tol, _ip(st))
+        if scale_even != 1.0 or scale_odd != 1.0:
+            res = self.L.ref_solve_scaled(_dp(x), _dp(b), tol, scale_even, scale_odd, _ip(st))
+        else:
+            res = self.L.ref_solve(_dp(x), _dp(b), tol, _ip(st))
         return x, res, st
+
+    def shift_mass(self, m0):
+        """shift_update (src/dirac.c:669-691): new mass on every level of the hierarchy."""
+        self.L.ref_shift_mass(float(m0))
 
     def solve_mt(self, b, tol=1e-10):
         b = np.ascontiguousarray(b, dtype=np.complex128)

@@ -70,6 +70,20 @@ double ref_solve(double *out, double *in, double tol, int *status) {
   return dd_alpha_amg_wilson_solve(out, in, tol, 1.0, 1.0, status);
 }
 
+/* same entry with the clover scaling by site parity (scale_clover, src/dirac.c:646-667) */
+double ref_solve_scaled(double *out, double *in, double tol, double scale_even, double scale_odd, int *status) {
+  return dd_alpha_amg_wilson_solve(out, in, tol, scale_even, scale_odd, status);
+}
+
+/* mass shift on every level: shift_update (src/dirac.c:669-691), as run_dd_alpha_amg_setup_if_necessary does
+ * (src/dd_alpha_amg.c:91-92) */
+void ref_shift_mass(double m0) {
+#pragma omp parallel num_threads(threading[0]->n_core)
+  {
+    shift_update((complex_double)m0, &l, threading[omp_get_thread_num()]);
+  }
+}
+
 /* multi-threaded solve: wilson_driver (src/top_level.c:64) inside a parallel region as in src/main.c:99 */
 double ref_solve_mt(double *out, double *in, double tol, int *status, double *seconds) {
   int n = 2*l.inner_vector_size;
