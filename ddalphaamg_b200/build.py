@@ -46,19 +46,24 @@ def _compile_all(srcs, objdir, cmd_for, jobs=8):
     return objs
 
 
-def build(verbose=False):
+def build(verbose=False, nofuse=False):
+    """nofuse=True: measurement build libdd_alpha_amg_nofuse.so with the round-1 (unfused) complex multiply-adds, loaded
+    only through DDA_LIBRARY for A/B timings of the same kernels."""
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
-    objdir = os.path.join(HERE, "build", "cuda")
+    objdir = os.path.join(HERE, "build", "cuda_nofuse" if nofuse else "cuda")
+    lib = os.path.join(HERE, "libdd_alpha_amg_nofuse.so") if nofuse else LIB
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--extended-lambda",
              "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "--use_fast_math=false", "-I" + os.path.join(ROOT, "include")]
     flags = [f for f in flags if f != "--use_fast_math=false"]
+    if nofuse:
+        flags += ["-DDDA_NO_FUSE"]
     if verbose:
         flags += ["-Xptxas", "-v"]
     objs = _compile_all(srcs, objdir, lambda s, o: ["nvcc"] + flags + ["-c", s, "-o", o])
-    if _newer(LIB, objs):
-        subprocess.check_call(["nvcc", "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+    if _newer(lib, objs):
+        subprocess.check_call(["nvcc", "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
                                                                        "-Xcompiler", "-fopenmp", "-lcudart", "-lnccl"])
-    return LIB
+    return lib
 
 
 def build_emu():
@@ -75,4 +80,4 @@ if __name__ == "__main__":
     if "--emu" in sys.argv:
         print(build_emu())
     else:
-        print(build(verbose="-v" in sys.argv))
+        print(build(verbose="-v" in sys.argv, nofuse="--nofuse" in sys.argv))

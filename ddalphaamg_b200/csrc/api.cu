@@ -317,6 +317,7 @@ int dda_info(int what, int depth) {
   Solver &s = A->s;
   int nl = s.setup_done ? s.nlev : 1;
   if (what == DDA_INFO_NUM_LEVELS) return s.setup_done ? s.nlev : s.p.num_levels;
+  if (what == DDA_INFO_COARSEST_REPLICATED) return (s.setup_done && s.cst.active && s.cst.replicated) ? 1 : 0;
   if (what == DDA_INFO_EMULATION) {
 #ifdef DDA_HOST_EMU
     return 1;
@@ -498,13 +499,18 @@ double dda_bench_op(int op, int depth, int reps) {
       case DDA_BENCH_INTERPOLATE: tr_interpolate(L.tr, L.vx, s.lev[depth + 1].vx, false); break;
       case DDA_BENCH_SMOOTHER: mg_smoother(s, depth, L.vx, L.vb, s.p.post_smooth_iter[depth], false); break;
       case DDA_BENCH_VCYCLE: mg_vcycle(s, depth, L.w[9], L.vb, true); break;
+      case DDA_BENCH_COARSEST_SCHUR: mg_coarsest_schur(s, s.cst.x, s.cst.b, nullptr); break;
       default: fatal("dda_bench_op: unknown op", __FILE__, __LINE__);
     }
   };
   // deterministic non-trivial input
   if (op == DDA_BENCH_DW_DOUBLE) { cd *x = s.xb; launch_n(n, DLAMBDA(long i) { x[i] = cd(1.0 + 1e-3 * (double)(i % 97), 0.5 - 1e-3 * (double)(i % 89)); }); }
   else if (op == DDA_BENCH_DW_FLOAT) { cf *x = (cf *)s.xb; launch_n(n, DLAMBDA(long i) { x[i] = cf(1.f + 1e-3f * (float)(i % 97), 0.5f - 1e-3f * (float)(i % 89)); }); }
-  else {
+  else if (op == DDA_BENCH_COARSEST_SCHUR) {
+    DDA_ASSERT(s.setup_done && s.cst.active && s.p.odd_even);
+    cf *x = s.cst.b; const long ne = s.cst.op->n_even * s.cst.op->n;
+    launch_n(ne, DLAMBDA(long i) { x[i] = cf(1.f + 1e-3f * (float)(i % 97), 0.5f - 1e-3f * (float)(i % 89)); });
+  } else {
     DDA_ASSERT(s.setup_done);
     cf *x = L.vb; launch_n(n, DLAMBDA(long i) { x[i] = cf(1.f + 1e-3f * (float)(i % 97), 0.5f - 1e-3f * (float)(i % 89)); });
     if (op == DDA_BENCH_INTERPOLATE) { Level &N = s.lev[depth + 1]; cf *y = N.vx; launch_n(N.geo.vlen(), DLAMBDA(long i) { y[i] = cf(1.f + 1e-3f * (float)(i % 97), 0.5f - 1e-3f * (float)(i % 89)); }); }

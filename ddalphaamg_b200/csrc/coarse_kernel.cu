@@ -104,38 +104,8 @@ k_coarse_full(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
       mbar_wait(&full[st], (uint32_t)((j / STAGES) & 1));
       const cf *M = Ms + (size_t)st * nn;
       if (active) {
-        {                                 // forward
-          const float4 *v4 = reinterpret_cast<const float4 *>(vec + m * n + grp * ch);
-          const cf *Mb = M + (size_t)(grp * ch) * n + 2 * p;
-#pragma unroll 2
-          for (int cc = 0; cc < ch; cc += 2) {
-            const float4 v = v4[cc >> 1];
-            const float4 m0 = *reinterpret_cast<const float4 *>(Mb + (size_t)cc * n);
-            const float4 m1 = *reinterpret_cast<const float4 *>(Mb + (size_t)(cc + 1) * n);
-            cmac(f0r, f0i, m0.x, m0.y, v.x, v.y);
-            cmac(f1r, f1i, m0.z, m0.w, v.x, v.y);
-            cmac(f0r, f0i, m1.x, m1.y, v.z, v.w);
-            cmac(f1r, f1i, m1.z, m1.w, v.z, v.w);
-          }
-        }
-        if (m > 0) {                      // daggered: conj(M[r][c]) w[r]
-          const cf *w = vec + 5 * n;
-          const cf *M0 = M + (size_t)(2 * p) * n, *M1 = M0 + n;
-          float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;
-          int ip = grp * (ch >> 1) + p; if (ip >= P) ip -= P;    // rotated row pair
-#pragma unroll 2
-          for (int i = 0; i < (ch >> 1); i++) {
-            const float4 wv = *reinterpret_cast<const float4 *>(w + 2 * ip);
-            const float4 m0 = *reinterpret_cast<const float4 *>(M0 + 2 * ip);
-            const float4 m1 = *reinterpret_cast<const float4 *>(M1 + 2 * ip);
-            cmacc(a0r, a0i, m0.x, m0.y, wv.x, wv.y);
-            cmacc(a0r, a0i, m0.z, m0.w, wv.z, wv.w);
-            cmacc(a1r, a1i, m1.x, m1.y, wv.x, wv.y);
-            cmacc(a1r, a1i, m1.z, m1.w, wv.z, wv.w);
-            ip++; if (ip == P) ip = 0;
-          }
-          zr[m - 1][0] = a0r; zi[m - 1][0] = a0i; zr[m - 1][1] = a1r; zi[m - 1][1] = a1i;
-        }
+        blk_forward(M, vec + m * n, n, grp, ch, p, f0r, f0i, f1r, f1i);
+        if (m > 0) blk_dagger(M, vec + 5 * n, n, grp, ch, p, zr[m - 1][0], zi[m - 1][0], zr[m - 1][1], zi[m - 1][1]);   // conj(M[r][c]) w[r]
       }
       __syncthreads();
       if (tid == 0 && j + STAGES < total) issue(j + STAGES);
@@ -256,38 +226,14 @@ k_coarse_sap_mr(CoarseOp op, cf *__restrict__ x, const cf *__restrict__ rin, con
       if (active) {
         {                                 // forward: Dr[i] += M v,  v = r[i] (self coupling) or r[j] (link)
           const int src = (jb.type == 0) ? jb.i : jb.j;
-          const float4 *v4 = reinterpret_cast<const float4 *>(rv + src * n + grp * ch);
-          const cf *Mb = M + (size_t)(grp * ch) * n + 2 * p;
           float f0r = 0.f, f0i = 0.f, f1r = 0.f, f1i = 0.f;
-#pragma unroll 2
-          for (int cc = 0; cc < ch; cc += 2) {
-            const float4 v = v4[cc >> 1];
-            const float4 m0 = *reinterpret_cast<const float4 *>(Mb + (size_t)cc * n);
-            const float4 m1 = *reinterpret_cast<const float4 *>(Mb + (size_t)(cc + 1) * n);
-            cmac(f0r, f0i, m0.x, m0.y, v.x, v.y);
-            cmac(f1r, f1i, m0.z, m0.w, v.x, v.y);
-            cmac(f0r, f0i, m1.x, m1.y, v.z, v.w);
-            cmac(f1r, f1i, m1.z, m1.w, v.z, v.w);
-          }
+          blk_forward(M, rv + src * n, n, grp, ch, p, f0r, f0i, f1r, f1i);
           float *d = reinterpret_cast<float *>(Dr + jb.i * n + 2 * p);
           atomicAdd(d, f0r); atomicAdd(d + 1, f0i); atomicAdd(d + 2, f1r); atomicAdd(d + 3, f1i);
         }
         if (jb.type > 0) {                // daggered: Dr[j] += gamma5 M^H gamma5 r[i]
-          const cf *wv_ = rg + jb.i * n;
-          const cf *M0 = M + (size_t)(2 * p) * n, *M1 = M0 + n;
-          float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;
-          int ip = grp * (ch >> 1) + p; if (ip >= P) ip -= P;
-#pragma unroll 2
-          for (int i = 0; i < (ch >> 1); i++) {
-            const float4 wv = *reinterpret_cast<const float4 *>(wv_ + 2 * ip);
-            const float4 m0 = *reinterpret_cast<const float4 *>(M0 + 2 * ip);
-            const float4 m1 = *reinterpret_cast<const float4 *>(M1 + 2 * ip);
-            cmacc(a0r, a0i, m0.x, m0.y, wv.x, wv.y);
-            cmacc(a0r, a0i, m0.z, m0.w, wv.z, wv.w);
-            cmacc(a1r, a1i, m1.x, m1.y, wv.x, wv.y);
-            cmacc(a1r, a1i, m1.z, m1.w, wv.z, wv.w);
-            ip++; if (ip == P) ip = 0;
-          }
+          float a0r, a0i, a1r, a1i;
+          blk_dagger(M, rg + jb.i * n, n, grp, ch, p, a0r, a0i, a1r, a1i);
           float *d = reinterpret_cast<float *>(Dr + jb.j * n + 2 * p);
           atomicAdd(d, sgc * a0r); atomicAdd(d + 1, sgc * a0i); atomicAdd(d + 2, sgc * a1r); atomicAdd(d + 3, sgc * a1i);
         }

@@ -66,7 +66,7 @@ template <class T> HD cx<T> conj(cx<T> a) { return cx<T>(a.re, -a.im); }
 template <class T> HD T norm2(cx<T> a) { return a.re * a.re + a.im * a.im; }
 // fused multiply-add on reals: fma() on the device (one FFMA/DFMA; without it `a += b*c - d*e` compiles to
 // FMUL + FFMA + FADD because the compiler may not re-associate), plain expression in the host-emulation build
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(DDA_NO_FUSE)
 HD float fma_r(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 HD double fma_r(double a, double b, double c) { return __fma_rn(a, b, c); }
 #else
@@ -74,10 +74,17 @@ HD float fma_r(float a, float b, float c) { return a * b + c; }
 HD double fma_r(double a, double b, double c) { return a * b + c; }
 #endif
 // a += b*c ; a += conj(b)*c ; a -= b*c ; a -= conj(b)*c      (4 fused multiply-adds each)
+#ifdef DDA_NO_FUSE   // measurement build only (build.py --nofuse): the round-1 expressions, FMUL + FFMA + FADD per component
+template <class T> HD void fma_(cx<T> &a, cx<T> b, cx<T> c) { a.re += b.re * c.re - b.im * c.im; a.im += b.re * c.im + b.im * c.re; }
+template <class T> HD void fmac_(cx<T> &a, cx<T> b, cx<T> c) { a.re += b.re * c.re + b.im * c.im; a.im += b.re * c.im - b.im * c.re; }
+template <class T> HD void fms_(cx<T> &a, cx<T> b, cx<T> c) { a.re -= b.re * c.re - b.im * c.im; a.im -= b.re * c.im + b.im * c.re; }
+template <class T> HD void fmsc_(cx<T> &a, cx<T> b, cx<T> c) { a.re -= b.re * c.re + b.im * c.im; a.im -= b.re * c.im - b.im * c.re; }
+#else
 template <class T> HD void fma_(cx<T> &a, cx<T> b, cx<T> c) { a.re = fma_r(-b.im, c.im, fma_r(b.re, c.re, a.re)); a.im = fma_r(b.im, c.re, fma_r(b.re, c.im, a.im)); }
 template <class T> HD void fmac_(cx<T> &a, cx<T> b, cx<T> c) { a.re = fma_r(b.im, c.im, fma_r(b.re, c.re, a.re)); a.im = fma_r(-b.im, c.re, fma_r(b.re, c.im, a.im)); }
 template <class T> HD void fms_(cx<T> &a, cx<T> b, cx<T> c) { a.re = fma_r(b.im, c.im, fma_r(-b.re, c.re, a.re)); a.im = fma_r(-b.im, c.re, fma_r(-b.re, c.im, a.im)); }
 template <class T> HD void fmsc_(cx<T> &a, cx<T> b, cx<T> c) { a.re = fma_r(-b.im, c.im, fma_r(-b.re, c.re, a.re)); a.im = fma_r(b.im, c.re, fma_r(-b.re, c.im, a.im)); }
+#endif
 // multiply by a unit: code 0:+1 1:-1 2:+i 3:-i
 template <int CODE, class T> HD cx<T> mul_unit(cx<T> z) {
   if (CODE == 0) return z;

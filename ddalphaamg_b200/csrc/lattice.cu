@@ -164,6 +164,30 @@ void Geometry::build() {
     nsapjobs = (int)(jobs.size() / 4);
     d_sapjobs = dev_upload(jobs);
   }
+  // fused fine SAP kernel (sap_kernel.cu, v2): structure of one 4^4 even-odd block, identical for every block
+  if (block_eo && !last && bs == 256 && bs_even == 128) {
+    std::vector<unsigned> tab(5 * 256, 0u);
+    int slot[4][256], cnt[4] = {0, 0, 0, 0};
+    for (int l = 0; l < 256; l++) for (int m = 0; m < 4; m++) slot[m][l] = ((bf[l] >> m) & 1) ? 255 : cnt[m]++;
+    for (int m = 0; m < 4; m++) DDA_ASSERT(cnt[m] == 192);
+    for (int l = 0; l < 256; l++) {
+      unsigned in = (~(unsigned)bf[l]) & 0xFFu, nf = 0, nbk = 0, lf = 0, lb = 0;
+      for (int m = 0; m < 4; m++) {
+        if (in & (1u << m)) {
+          const int n = h_nb[(long)m * V + l];
+          DDA_ASSERT(n >= 0 && n < 256 && ((n < 128) != (l < 128)));
+          nf |= (unsigned)(n & 127) << (8 * m); lf |= (unsigned)slot[m][l] << (8 * m);
+        }
+        if (in & (1u << (4 + m))) {
+          const int n = h_nb[(long)(4 + m) * V + l];
+          DDA_ASSERT(n >= 0 && n < 256 && ((n < 128) != (l < 128)) && slot[m][n] < 192);
+          nbk |= (unsigned)(n & 127) << (8 * m); lb |= (unsigned)slot[m][n] << (8 * m);
+        }
+      }
+      tab[5 * l] = in; tab[5 * l + 1] = nf; tab[5 * l + 2] = nbk; tab[5 * l + 3] = lf; tab[5 * l + 4] = lb;
+    }
+    d_saptab = dev_upload(tab);
+  }
   // sites / blocks on the rank boundary (used to overlap the halo exchange with interior work)
   {
     std::vector<char> isb(V, 0);
@@ -192,6 +216,7 @@ void Geometry::destroy() {
   dev_free(d_bnd); d_bnd = nullptr;
   dev_free(d_nbg); d_nbg = nullptr;
   dev_free(d_sapjobs); d_sapjobs = nullptr; nsapjobs = 0;
+  dev_free(d_saptab); d_saptab = nullptr;
   for (int c = 0; c < 2; c++) { dev_free(d_blocklist_int[c]); dev_free(d_blocklist_bnd[c]); d_blocklist_int[c] = d_blocklist_bnd[c] = nullptr; }
   d_nb = nullptr; d_blkflag = d_aggflag = nullptr; d_lex2nat = d_nat2lex = nullptr;
   d_blocklist[0] = d_blocklist[1] = nullptr; d_agg2coarse = nullptr;

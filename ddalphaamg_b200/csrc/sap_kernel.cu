@@ -23,6 +23,7 @@
 #include "solver.h"
 #include "fine_op.cuh"
 #include "halo.h"
+#include "tma.cuh"
 
 namespace dda {
 
@@ -243,7 +244,7 @@ struct SiteRef {       // everything that identifies one of the thread pair's tw
 // first_zero: x == 0 on the whole lattice on entry (first colour of a zero-guess call): r = eta, x = e.
 __global__ void __launch_bounds__(BS, 2)
 k_sap_fine(FineOp<float> op, cf *x, const cf *__restrict__ eta, const int *__restrict__ blocklist, int biter, int first_zero) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   Shared &sm = *reinterpret_cast<Shared *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   Ctx cx_;
@@ -394,6 +395,307 @@ k_sap_fine(FineOp<float> op, cf *x, const cf *__restrict__ eta, const int *__res
   }
 }
 
+
+// ===================================================================================================================
+// Version 2 of the fused block visit (default; DDA_SAP_V1=1 selects k_sap_fine above).
+//
+// What changed against v1 (ncu of v1: 52 % issue utilisation, 150 k warp instructions per visit, top stall = L2 latency
+// of the clover stream, 377 KB DRAM per visit):
+//  * the clover blocks of the even sites and the inverse blocks of the odd sites are STAGED IN SHARED MEMORY by one TMA
+//    bulk copy each (the 128 sites of one parity are 4 contiguous 32-site tiles = 36 864 B), issued as soon as the
+//    previous contents are consumed, so the copy engine fetches the next operand block while the in-block hops run;
+//  * room for that buffer: only the 768 in-block links are kept in shared memory (a 4^4 block has 1024 links, the 256
+//    that leave the block are only needed once, by the residual, and are read from global memory there), and the exchange
+//    buffer holds one parity at a time;
+//  * the clover term of the odd sites is never applied: with r'_o = eta_o - (N x)_o the block solve needs only
+//    Coo^-1 r'_o - x_o and Coo^-1 (r'_o - N_oe e_e)  (algebraically the same iterates), so C_oo is not read at all;
+//  * r'_o is parked in the odd sites' slots of x itself (dead until the final write) instead of shared memory;
+//  * all complex multiply-adds are 4 FFMA (common.cuh fma_).
+// Shared memory: links 55 296 + exchange 12 288 + clover 36 864 + reductions 256 + barrier 8 = 104 712 B -> 2 CTAs / SM.
+struct Shared2 {
+  float Cb[4 * 72 * 32];            // clover (even sites) or inverse clover (odd sites) of the block, tile layout
+  float2 U[4][9][192];              // in-block links: [mu][3*row+col][slot of the link's source site]
+  float2 Vb[12][BS / 2];            // exchange buffer [component][site of ONE parity]
+  float red[2][BS / 32][4];
+  unsigned long long bar;
+};
+
+struct Site2 {                      // one of the thread pair's two sites; packed bytes, one per direction
+  int l;                            // block-local index
+  unsigned in;                      // in-block mask (bit d: neighbour d is inside the block)
+  unsigned nf, nb;                  // exchange-buffer index (0..127) of the +mu / -mu neighbour
+  unsigned lf, lb;                  // link slot of U_mu(site) / U_mu(site - mu)
+};
+
+template <int MU>
+__device__ __forceinline__ void sm_hop_pair2(const Shared2 &sm, const float2 *vu, const float2 *vl, float sg, const Site2 &R,
+                                             cf *up, cf *lowA, cf *lowB) {
+  if (R.in & (1u << MU)) {
+    const int n = (R.nf >> (8 * MU)) & 0xFF, u = (R.lf >> (8 * MU)) & 0xFF;
+    cf pu[3], pl[3], M[9];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { pu[c] = ld2(vu[c * (BS / 2) + n]); pl[c] = ld2(vl[c * (BS / 2) + n]); }
+#pragma unroll
+    for (int k = 0; k < 9; k++) M[k] = ld2(sm.U[MU][k][u]);
+    half_hop<MU, +1>(pu, pl, M, sg, up, lowA, lowB);
+  }
+  if (R.in & (1u << (4 + MU))) {
+    const int n = (R.nb >> (8 * MU)) & 0xFF, u = (R.lb >> (8 * MU)) & 0xFF;
+    cf pu[3], pl[3], M[9];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { pu[c] = ld2(vu[c * (BS / 2) + n]); pl[c] = ld2(vl[c * (BS / 2) + n]); }
+#pragma unroll
+    for (int k = 0; k < 9; k++) M[k] = ld2(sm.U[MU][k][u]);
+    half_hop<MU, -1>(pu, pl, M, sg, up, lowA, lowB);
+  }
+}
+
+// y = N v for site R (in-block hops only); v (opposite parity) is in the exchange buffer
+__device__ __forceinline__ void sm_hops2(const Shared2 &sm, const Ctx &cx_, const Site2 &R, cf *y) {
+  cf up[3], lowA[3], lowB[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) { up[c] = cf(0.f, 0.f); lowA[c] = cf(0.f, 0.f); lowB[c] = cf(0.f, 0.f); }
+  const float2 *vu = &sm.Vb[cx_.up][0], *va = &sm.Vb[cx_.loA][0], *vb = &sm.Vb[cx_.loB][0];
+  sm_hop_pair2<0>(sm, vu, va, cx_.sg, R, up, lowA, lowB);
+  sm_hop_pair2<1>(sm, vu, vb, cx_.sg, R, up, lowA, lowB);
+  sm_hop_pair2<2>(sm, vu, vb, cx_.sg, R, up, lowA, lowB);
+  sm_hop_pair2<3>(sm, vu, va, cx_.sg, R, up, lowA, lowB);
+  pair_combine(up, lowA, lowB, y);
+}
+
+__device__ __forceinline__ void put2(Shared2 &sm, const Ctx &cx_, int h, const cf *v) {   // h: index inside the parity (0..127)
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    sm.Vb[cx_.up + c][h] = make_float2(v[c].re, v[c].im);
+    sm.Vb[cx_.loA + c][h] = make_float2(v[3 + c].re, v[3 + c].im);
+  }
+}
+
+// clov_half with the packed blocks in shared memory (Cs already offset by tile and lane, stride 32 floats per entry)
+__device__ __forceinline__ void clov_half_sm(const float *Cs, const Ctx &cx_, const cf *x, cf *y) {
+  cf xm[3], xo[3], xmn[3], xon[3], ylo[3], yhi[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    xm[c] = x[c]; xmn[c] = x[3 + c];
+    xo[c] = cf(__shfl_xor_sync(0xffffffffu, x[c].re, 16), __shfl_xor_sync(0xffffffffu, x[c].im, 16));
+    xon[c] = cf(__shfl_xor_sync(0xffffffffu, x[3 + c].re, 16), __shfl_xor_sync(0xffffffffu, x[3 + c].im, 16));
+    ylo[c] = cf(0.f, 0.f); yhi[c] = cf(0.f, 0.f);
+  }
+  const int s = cx_.s;
+  const float cj = -cx_.sg;          // +1 for s = 0 (entries used as stored), -1 for s = 1 (conjugated)
+#pragma unroll 1
+  for (int b = 0; b < 2; b++) {
+    const float *Cd = Cs + ((6 * b + 3 * s) << 5), *Ct = Cs + ((12 + 30 * b) << 5);
+    cf yo[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) yo[i] = Cd[i << 5] * xm[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = i + 1; j < 3; j++) {
+        const int m = s ? tri(3 + i, 3 + j) : tri(i, j);
+        const cf a(Ct[(2 * m) << 5], Ct[(2 * m + 1) << 5]);
+        fma_(yo[i], a, xm[j]);
+        fmac_(yo[j], a, xm[i]);
+      }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int m = s ? tri(j, 3 + i) : tri(i, 3 + j);
+        const cf a(Ct[(2 * m) << 5], cj * Ct[(2 * m + 1) << 5]);
+        fma_(yo[i], a, xo[j]);
+      }
+#pragma unroll
+    for (int c = 0; c < 3; c++) { ylo[c] = yhi[c]; yhi[c] = yo[c]; xm[c] = xmn[c]; xo[c] = xon[c]; }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; c++) { y[c] = ylo[c]; y[3 + c] = yhi[c]; }
+}
+
+__device__ __forceinline__ void store_own(cf *v, long base, const Ctx &cx_, const cf *val) {
+#pragma unroll
+  for (int c = 0; c < 3; c++) { v[base + ((long)(cx_.up + c) << 5)] = val[c]; v[base + ((long)(cx_.loA + c) << 5)] = val[3 + c]; }
+}
+
+// tab: per block-local site 5 words {in, nf, nb, lf, lb} (identical for every block, built on the host)
+__global__ void __launch_bounds__(BS, 2)
+k_sap_fine2(FineOp<float> op, cf *x, const cf *__restrict__ eta, const int *__restrict__ blocklist, const unsigned *__restrict__ tab,
+            int biter, int first_zero) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Shared2 &sm = *reinterpret_cast<Shared2 *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  Ctx cx_;
+  cx_.s = lane >> 4; cx_.sg = cx_.s ? 1.f : -1.f;
+  cx_.up = 3 * cx_.s; cx_.loA = 6 + 3 * cx_.s; cx_.loB = 6 + 3 * (1 - cx_.s);
+  const long base = (long)blocklist[blockIdx.x] * BS;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(&sm.bar);
+  const uint32_t CB_BYTES = 4 * 72 * 32 * sizeof(float);
+  // clover stream: load number q (0, 1, 2, ...) completes phase q of the barrier
+  const float *srcCe = op.C + (base >> 5) * (72L << 5);                 // even sites: first 4 tiles of the block
+  const float *srcCinvO = op.Cinv + ((base + BS / 2) >> 5) * (72L << 5);  // odd sites: last 4 tiles
+  uint32_t cphase = 0;
+  auto cload = [&](const float *src) {                                    // thread 0 only, after a block-wide barrier
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(bar, CB_BYTES);
+    tma_bulk_g2s(sm.Cb, src, CB_BYTES, bar);
+  };
+  auto cwait = [&]() { mbar_wait(bar, cphase & 1); cphase++; };
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    cload(first_zero ? srcCinvO : srcCe);
+  }
+
+  // in-block links of the block -> shared memory: thread tid copies the links of site tid (coalesced 256 B rows)
+  {
+    const float2 *D2 = reinterpret_cast<const float2 *>(op.D);
+    const long st = base + tid;
+    const long u = (st >> 5) * (36L << 5) + (st & 31);
+    const unsigned slots = __ldg(tab + 5 * tid + 3), inb = __ldg(tab + 5 * tid);
+#pragma unroll
+    for (int mu = 0; mu < 4; mu++)
+      if (inb & (1u << mu)) {
+        const int sl = (slots >> (8 * mu)) & 0xFF;
+#pragma unroll
+        for (int k = 0; k < 9; k++) sm.U[mu][k][sl] = __ldg(D2 + u + ((long)(9 * mu + k) << 5));
+      }
+  }
+  Site2 E, O;
+  E.l = 16 * w + (lane & 15); O.l = BS / 2 + E.l;
+  {
+    const unsigned *te = tab + 5 * E.l, *to = tab + 5 * O.l;
+    E.in = __ldg(te); E.nf = __ldg(te + 1); E.nb = __ldg(te + 2); E.lf = __ldg(te + 3); E.lb = __ldg(te + 4);
+    O.in = __ldg(to); O.nf = __ldg(to + 1); O.nb = __ldg(to + 2); O.lf = __ldg(to + 3); O.lb = __ldg(to + 4);
+  }
+  const long sE = base + E.l, sO = base + O.l;
+  const long vE = (sE >> 5) * (12L << 5) + (sE & 31), vO = (sO >> 5) * (12L << 5) + (sO & 31);
+  const float *CsT = sm.Cb + (E.l >> 5) * (72 * 32) + (E.l & 31);       // same tile / lane for the even and the odd site
+
+  cf rE[6], rO[6];
+  load_own(eta, vE, cx_, rE); load_own(eta, vO, cx_, rO);
+  __syncthreads();                                                      // links and barrier initialisation visible
+  if (!first_zero) {
+    // r_e = eta_e - C_e x_e - (N x)_e ,  r'_o = eta_o - (N x)_o : couplings to neighbouring blocks from global memory,
+    // in-block hops through the exchange buffer, one parity at a time
+    cf xe[6], y[6];
+    load_own(x, vE, cx_, xe);
+    cwait();
+    clov_half_sm(CsT, cx_, xe, y);
+#pragma unroll
+    for (int c = 0; c < 6; c++) rE[c] -= y[c];
+    put2(sm, cx_, E.l, xe);
+    gl_hops(op, cx_, sE, (~E.in) & 0xFFu, x, y);
+#pragma unroll
+    for (int c = 0; c < 6; c++) rE[c] -= y[c];
+    gl_hops(op, cx_, sO, (~O.in) & 0xFFu, x, y);
+#pragma unroll
+    for (int c = 0; c < 6; c++) rO[c] -= y[c];
+    __syncthreads();                                                    // x_e in the buffer; C_e consumed by everybody
+    if (tid == 0) cload(srcCinvO);
+    sm_hops2(sm, cx_, O, y);                                            // N_oe x_e
+#pragma unroll
+    for (int c = 0; c < 6; c++) rO[c] -= y[c];
+    __syncthreads();
+    cf xo[6];
+    load_own(x, vO, cx_, xo);
+    put2(sm, cx_, E.l, xo);                                             // odd site O.l sits at index E.l of its parity
+    __syncthreads();
+    sm_hops2(sm, cx_, E, y);                                            // N_eo x_o
+#pragma unroll
+    for (int c = 0; c < 6; c++) rE[c] -= y[c];
+    __syncthreads();
+  }
+
+  // block solve.  k = 0: e_o = Coo^-1 r'_o - x_o, t_e = r_e - N_eo e_o.   k = 1..biter: one MR step on the Schur
+  // complement S = C_ee - N_eo Coo^-1 N_oe.   k = biter+1: x_o = Coo^-1 (r'_o - N_oe e_e), x_e += e_e.
+  cf tE[6], eE[6];
+#pragma unroll
+  for (int c = 0; c < 6; c++) { tE[c] = rE[c]; eE[c] = cf(0.f, 0.f); }
+#pragma unroll 1
+  for (int k = 0; k <= biter + 1; k++) {
+    cf wv[6], z[6];
+    if (k > 0) sm_hops2(sm, cx_, O, wv);                                // N_oe (t_e or e_e)
+    if (k == 0) {
+#pragma unroll
+      for (int c = 0; c < 6; c++) wv[c] = rO[c];
+      cwait();                                                          // Coo^-1 in the buffer (stays for k = 1)
+    } else if (k == biter + 1) {
+      cf ro[6];
+      load_own(x, vO, cx_, ro);                                         // parked r'_o
+#pragma unroll
+      for (int c = 0; c < 6; c++) wv[c] = ro[c] - wv[c];
+      if (biter > 0) cwait();
+    } else if (k > 1) cwait();
+    clov_half_sm(CsT, cx_, wv, z);
+    if (k == biter + 1) {
+      if (!first_zero) {
+        cf a[6];
+        load_own(x, vE, cx_, a);
+#pragma unroll
+        for (int c = 0; c < 6; c++) eE[c] += a[c];
+      }
+      store_own(x, vE, cx_, eE);
+      store_own(x, vO, cx_, z);
+      break;
+    }
+    if (k == 0) {
+      if (!first_zero) {
+        cf xo[6];
+        load_own(x, vO, cx_, xo);
+#pragma unroll
+        for (int c = 0; c < 6; c++) z[c] -= xo[c];                      // e_o = Coo^-1 r'_o - x_o
+      }
+      store_own(x, vO, cx_, rO);                                        // park r'_o (x_o is dead until the final write)
+    } else {
+#pragma unroll
+      for (int c = 0; c < 6; c++) z[c] = -z[c];                         // a2_o = -Coo^-1 N_oe t_e
+    }
+    __syncthreads();                                                    // everybody is done with the even buffer and with Coo^-1
+    if (tid == 0 && k > 0) cload(srcCe);
+    put2(sm, cx_, E.l, z);
+    __syncthreads();
+    cf y[6];
+    sm_hops2(sm, cx_, E, y);                                            // N_eo (e_o or a2_o)
+    if (k == 0) {
+#pragma unroll
+      for (int c = 0; c < 6; c++) tE[c] -= y[c];
+      __syncthreads();                                                  // odd buffer consumed
+    } else {
+      cf Dr[6];
+      cwait();
+      clov_half_sm(CsT, cx_, tE, Dr);
+#pragma unroll
+      for (int c = 0; c < 6; c++) Dr[c] += y[c];
+      // alpha = <Dr,t>/<Dr,Dr> over the even sites of the block (local_minres, linsolve_generic.c:1013-1022)
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        p0 = __fmaf_rn(Dr[c].im, tE[c].im, __fmaf_rn(Dr[c].re, tE[c].re, p0));
+        p1 = __fmaf_rn(-Dr[c].im, tE[c].re, __fmaf_rn(Dr[c].re, tE[c].im, p1));
+        p2 = __fmaf_rn(Dr[c].im, Dr[c].im, __fmaf_rn(Dr[c].re, Dr[c].re, p2));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+      }
+      float (*red)[4] = sm.red[k & 1];
+      if (lane == 0) { red[w][0] = p0; red[w][1] = p1; red[w][2] = p2; }
+      __syncthreads();                                                  // also: odd buffer and C_ee consumed by everybody
+      if (tid == 0) cload(srcCinvO);
+      p0 = p1 = p2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < BS / 32; i++) { p0 += red[i][0]; p1 += red[i][1]; p2 += red[i][2]; }
+      cf alpha(0.f, 0.f);
+      if (p2 > 1e-30f) alpha = cf(p0 / p2, p1 / p2);
+#pragma unroll
+      for (int c = 0; c < 6; c++) { fma_(eE[c], alpha, tE[c]); fms_(tE[c], alpha, Dr[c]); }
+    }
+    put2(sm, cx_, E.l, (k < biter) ? tE : eE);
+    __syncthreads();
+  }
+}
+
 }  // namespace sap
 
 // fine-level SAP with the fused block kernel; same iteration as the generic path of mg_smoother
@@ -406,12 +708,20 @@ void sap_fine_fast(Solver &s, cf *x, const cf *eta, int iters, bool zero_guess) 
   Level &L = s.lev[0];
   const Geometry &g = L.geo;
   const int biter = s.p.block_iter[0];
-  static bool attr_set = false;
-  const int smem = (int)sizeof(sap::Shared);
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(sap::k_sap_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+  static int version = 0;
+  if (!version) {
+    const char *e = getenv("DDA_SAP_V1");
+    version = (e && atoi(e) != 0) ? 1 : 2;
+    CUDA_CHECK(cudaFuncSetAttribute(sap::k_sap_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sap::Shared)));
+    CUDA_CHECK(cudaFuncSetAttribute(sap::k_sap_fine2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sap::Shared2)));
   }
+  const bool v2 = version == 2 && g.d_saptab;
+  auto launch = [&](const int *list, int nblk, int first) {
+    if (nblk <= 0) return;
+    if (v2) sap::k_sap_fine2<<<nblk, sap::BS, sizeof(sap::Shared2), g_stream>>>(L.opf, x, eta, list, g.d_saptab, biter, first);
+    else sap::k_sap_fine<<<nblk, sap::BS, sizeof(sap::Shared), g_stream>>>(L.opf, x, eta, list, biter, first);
+    g_launch_count++;
+  };
   if (zero_guess) vzero(x, g.vlen());
   for (int cyc = 0; cyc < iters; cyc++)
     for (int col = 0; col < 2; col++) {
@@ -419,21 +729,14 @@ void sap_fine_fast(Solver &s, cf *x, const cf *eta, int iters, bool zero_guess) 
       if (nblk == 0) continue;
       const int first = (zero_guess && cyc == 0 && col == 0) ? 1 : 0;
       if (first || !g.partitioned()) {
-        sap::k_sap_fine<<<nblk, sap::BS, smem, g_stream>>>(L.opf, x, eta, g.d_blocklist[col], biter, first);
-        g_launch_count++;
+        launch(g.d_blocklist[col], nblk, first);
       } else {
         // block residuals read x of neighbouring blocks on other ranks: exchange the ghost slabs on the second stream
         // while the blocks away from the rank boundary are solved, then the blocks that touch it
         halo_begin<cf>(g, x, 12, g.sh);
-        if (g.nblk_int[col] > 0) {
-          sap::k_sap_fine<<<g.nblk_int[col], sap::BS, smem, g_stream>>>(L.opf, x, eta, g.d_blocklist_int[col], biter, 0);
-          g_launch_count++;
-        }
+        launch(g.d_blocklist_int[col], g.nblk_int[col], 0);
         halo_end(g);
-        if (g.nblk_bnd[col] > 0) {
-          sap::k_sap_fine<<<g.nblk_bnd[col], sap::BS, smem, g_stream>>>(L.opf, x, eta, g.d_blocklist_bnd[col], biter, 0);
-          g_launch_count++;
-        }
+        launch(g.d_blocklist_bnd[col], g.nblk_bnd[col], 0);
       }
 #ifdef DDA_DEBUG_SYNC
       CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());

@@ -26,47 +26,13 @@ namespace dda {
 
 #ifndef DDA_HOST_EMU
 
-// forward product of the thread's row pair (2p, 2p+1) with the column chunk [grp*ch, grp*ch+ch) of the column-major block
-__device__ __forceinline__ void blk_forward(const cf *M, const cf *v, int n, int grp, int ch, int p, float &f0r, float &f0i, float &f1r, float &f1i) {
-  const float4 *v4 = reinterpret_cast<const float4 *>(v + grp * ch);
-  const cf *Mb = M + (size_t)(grp * ch) * n + 2 * p;
-#pragma unroll 2
-  for (int cc = 0; cc < ch; cc += 2) {
-    const float4 vv = v4[cc >> 1];
-    const float4 m0 = *reinterpret_cast<const float4 *>(Mb + (size_t)cc * n);
-    const float4 m1 = *reinterpret_cast<const float4 *>(Mb + (size_t)(cc + 1) * n);
-    cmac(f0r, f0i, m0.x, m0.y, vv.x, vv.y);
-    cmac(f1r, f1i, m0.z, m0.w, vv.x, vv.y);
-    cmac(f0r, f0i, m1.x, m1.y, vv.z, vv.w);
-    cmac(f1r, f1i, m1.z, m1.w, vv.z, vv.w);
-  }
-}
-// daggered product: columns 2p, 2p+1 of the block, conjugated, times the row chunk of w (walk rotated by p row pairs:
-// bank-conflict free stride-n accesses)
-__device__ __forceinline__ void blk_dagger(const cf *M, const cf *w, int n, int grp, int ch, int p, float &a0r, float &a0i, float &a1r, float &a1i) {
-  const int P = n >> 1;
-  const cf *M0 = M + (size_t)(2 * p) * n, *M1 = M0 + n;
-  int ip = grp * (ch >> 1) + p; if (ip >= P) ip -= P;
-#pragma unroll 2
-  for (int i = 0; i < (ch >> 1); i++) {
-    const float4 wv = *reinterpret_cast<const float4 *>(w + 2 * ip);
-    const float4 m0 = *reinterpret_cast<const float4 *>(M0 + 2 * ip);
-    const float4 m1 = *reinterpret_cast<const float4 *>(M1 + 2 * ip);
-    cmacc(a0r, a0i, m0.x, m0.y, wv.x, wv.y);
-    cmacc(a0r, a0i, m0.z, m0.w, wv.z, wv.w);
-    cmacc(a1r, a1i, m1.x, m1.y, wv.x, wv.y);
-    cmacc(a1r, a1i, m1.z, m1.w, wv.z, wv.w);
-    ip++; if (ip == P) ip = 0;
-  }
-}
-
 // phase 0: forward sites = odd, daggered sites = even.  phase 1: forward sites = even (plus S(x) self(x) when `self` is
 // given), daggered sites = odd.  in: vector read by both products (neighbour values for the forward sites, own value
 // for the daggered sites).
 template <int STAGES>
 __global__ void __launch_bounds__(128)
 k_schur_hop(CoarseOp op, int phase, const cf *__restrict__ in, const cf *__restrict__ self, cf *__restrict__ dir,
-            cf *__restrict__ Z, int nsites, int G, const int *__restrict__ skip) {
+            cf *__restrict__ Z, int nsites, int G, int rev, const int *__restrict__ skip) {
   if (skip && *skip) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = op.n, nn = n * n, nh = n / 2, P = n / 2, ch = n / G;
@@ -86,7 +52,10 @@ k_schur_hop(CoarseOp op, int phase, const cf *__restrict__ in, const cf *__restr
   }
   __syncthreads();
   const bool with_self = (phase == 1) && (self != nullptr);
-  auto site_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
+  // rev: walk the lattice backwards.  The two half applications of a Schur complement run in opposite directions, so the
+  // hop matrices streamed last by one are the first the next one needs: they are still in the 126 MB L2 (the operator of
+  // a 48^3 x 96 hierarchy is 238 MB), which saves about half of the DRAM traffic.
+  auto site_of = [&](int k) { const int q = (int)blockIdx.x + k * (int)gridDim.x; return rev ? nsites - 1 - q : q; };
   auto is_fwd = [&](int x) { return (x >= ne) == (phase == 0); };
   auto first_slot = [&](int x) { return (is_fwd(x) && with_self) ? 0 : 1; };   // slot 0 = S(x), slots 1..4 = F_mu(x)
   // producer (thread 0): next block to fetch = slot pm of the CTA's site number pk; pc = blocks issued so far
@@ -278,6 +247,7 @@ int sm_count() {
   return sms;
 }
 const int SCHUR_STAGES = 3;
+int g_schur_reverse = -1;
 }  // namespace
 
 bool schur_fast_supported(const CoarseOp &op) {
@@ -288,6 +258,7 @@ bool schur_fast_supported(const CoarseOp &op) {
 
 // one half application: forward sites get dir, daggered sites fill Z (see k_schur_hop)
 void schur_hop(const CoarseOp &op, int phase, const cf *in, const cf *self, cf *dir, cf *Z, const int *skip) {
+  if (g_schur_reverse < 0) { const char *e = getenv("DDA_SCHUR_REVERSE"); g_schur_reverse = e ? atoi(e) : 1; }
   const int n = op.n, G = pick_groups(n);
   const size_t nn = (size_t)n * n;
   const size_t smem = SCHUR_STAGES * nn * sizeof(cf) + (5 + 4 * G) * n * sizeof(cf) + 8 * sizeof(uint64_t);
@@ -297,7 +268,7 @@ void schur_hop(const CoarseOp &op, int phase, const cf *in, const cf *self, cf *
   if (per_sm > 8) per_sm = 8;
   DDA_ASSERT(per_sm >= 1);
   const long grid = std::min<long>(op.V, (long)sm_count() * per_sm);
-  k_schur_hop<SCHUR_STAGES><<<(unsigned)grid, 128, smem, g_stream>>>(op, phase, in, self, dir, Z, (int)op.V, G, skip);
+  k_schur_hop<SCHUR_STAGES><<<(unsigned)grid, 128, smem, g_stream>>>(op, phase, in, self, dir, Z, (int)op.V, G, g_schur_reverse ? phase : 0, skip);
   g_launch_count++;
 #ifdef DDA_DEBUG_SYNC
   CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());

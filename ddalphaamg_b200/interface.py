@@ -15,7 +15,7 @@ MAX_MG_LEVELS = 4
 
 
 class INFO:
-    NUM_LEVELS, SITES, SITE_VARS, TEST_VECTORS, BLOCK_SITES, NUM_BLOCKS, EMULATION = range(7)
+    NUM_LEVELS, SITES, SITE_VARS, TEST_VECTORS, BLOCK_SITES, NUM_BLOCKS, EMULATION, COARSEST_REPLICATED = range(8)
 
 
 class OPT:
@@ -33,7 +33,7 @@ class OP:
 
 
 class BENCH:
-    DW_DOUBLE, DW_FLOAT, LEVEL_APPLY, RESTRICT, INTERPOLATE, SMOOTHER, VCYCLE = range(7)
+    DW_DOUBLE, DW_FLOAT, LEVEL_APPLY, RESTRICT, INTERPOLATE, SMOOTHER, VCYCLE, COARSEST_SCHUR = range(8)
 
 
 CONF_INDEX_FCT = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
@@ -93,7 +93,8 @@ ALLREDUCE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int)
 
 
 def library_path():
-    return os.path.join(_HERE, "libdd_alpha_amg.so")
+    """The CUDA library.  DDA_LIBRARY (a path) selects another CUDA build of the same sources for A/B measurements."""
+    return os.environ.get("DDA_LIBRARY") or os.path.join(_HERE, "libdd_alpha_amg.so")
 
 
 _LIBS = {}

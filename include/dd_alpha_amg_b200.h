@@ -19,7 +19,8 @@ extern "C" {
 
 enum { DDA_DOUBLE = 0, DDA_FLOAT = 1 };
 enum { DDA_INFO_NUM_LEVELS = 0, DDA_INFO_SITES = 1, DDA_INFO_SITE_VARS = 2, DDA_INFO_TEST_VECTORS = 3,
-       DDA_INFO_BLOCK_SITES = 4, DDA_INFO_NUM_BLOCKS = 5, DDA_INFO_EMULATION = 6 };
+       DDA_INFO_BLOCK_SITES = 4, DDA_INFO_NUM_BLOCKS = 5, DDA_INFO_EMULATION = 6,
+       DDA_INFO_COARSEST_REPLICATED = 7 /* 1: the coarsest lattice is gathered and solved on every rank */ };
 enum { DDA_OPT_USE_FAST = 0, DDA_OPT_PROFILE = 1, DDA_OPT_SEED = 2, DDA_OPT_PRINT = 3 };
 enum { DDA_STAT_LAUNCHES = 0, DDA_STAT_DEVICE_BYTES = 1, DDA_STAT_PLAQUETTE = 2, DDA_STAT_ITER = 3,
        DDA_STAT_COARSE_ITER = 4, DDA_STAT_T_COARSEST = 5, DDA_STAT_T_RESTRICT = 6, DDA_STAT_T_INTERPOLATE = 7,
@@ -27,7 +28,8 @@ enum { DDA_STAT_LAUNCHES = 0, DDA_STAT_DEVICE_BYTES = 1, DDA_STAT_PLAQUETTE = 2,
 enum { DDA_OP_APPLY = 0, DDA_OP_RESTRICT = 1, DDA_OP_INTERPOLATE = 2, DDA_OP_SMOOTHER = 3, DDA_OP_VCYCLE = 4,
        DDA_OP_COARSEST_SOLVE = 5 };
 enum { DDA_BENCH_DW_DOUBLE = 0, DDA_BENCH_DW_FLOAT = 1, DDA_BENCH_LEVEL_APPLY = 2, DDA_BENCH_RESTRICT = 3,
-       DDA_BENCH_INTERPOLATE = 4, DDA_BENCH_SMOOTHER = 5, DDA_BENCH_VCYCLE = 6 };
+       DDA_BENCH_INTERPOLATE = 4, DDA_BENCH_SMOOTHER = 5, DDA_BENCH_VCYCLE = 6,
+       DDA_BENCH_COARSEST_SCHUR = 7 /* even-odd Schur complement of the coarsest operator (coarse_oddeven_generic.c:1162) */ };
 
 /* geometry of the hierarchy (reference: level_struct fields, main.h:263-341) */
 int dda_info(int what, int depth);
