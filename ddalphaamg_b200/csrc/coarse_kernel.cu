@@ -300,6 +300,55 @@ bool coarse_sap_mr_fast(const CoarseOp &op, cf *x, const cf *r, const int *d_blo
   return true;
 }
 
+// -------------------------------------------------------------------------------------------------------------------
+// Soo^-1 on the odd sites of the coarsest level: ONE CTA per site, the n x n block in shared memory in double, in-place
+// Gauss-Jordan without pivoting (the reference factorises LU without pivoting as well, coarse_oddeven_generic.c:24-73;
+// the explicit inverse replaces its forward / backward substitution, coarse_perform_fwd_bwd_subs :75-121).
+__global__ void __launch_bounds__(256) k_invert_self(CoarseOp op, long n_first, long nsites) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = op.n; const long nn = (long)n * n;
+  cd *A = reinterpret_cast<cd *>(smem_raw);                       // row-major [n][n]
+  cd *colp = A + nn;                                              // column p of the current step
+  const long o = blockIdx.x;
+  if (o >= nsites) return;
+  const cf *M = op.S + (n_first + o) * nn;
+  for (int q = threadIdx.x; q < nn; q += blockDim.x) { const int c = q / n, r = q - c * n; const cf v = M[q]; A[(long)r * n + c] = cd(v.re, v.im); }
+  __syncthreads();
+  for (int p = 0; p < n; p++) {
+    const cd piv = A[(long)p * n + p];
+    const double d = 1.0 / norm2(piv);
+    const cd ip(piv.re * d, -piv.im * d);
+    for (int r = threadIdx.x; r < n; r += blockDim.x) colp[r] = A[(long)r * n + p];
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += blockDim.x) A[(long)p * n + c] = (c == p) ? ip : A[(long)p * n + c] * ip;   // pivot row
+    __syncthreads();
+    for (int q = threadIdx.x; q < nn; q += blockDim.x) {
+      const int r = q / n, c = q - r * n;
+      if (r == p) continue;
+      const cd f = colp[r];
+      if (c == p) A[q] = -(f * ip);
+      else fms_(A[q], f, A[(long)p * n + c]);
+    }
+    __syncthreads();
+  }
+  cf *O = op.Sinv + o * nn;
+  for (int q = threadIdx.x; q < nn; q += blockDim.x) { const int c = q / n, r = q - c * n; const cd v = A[(long)r * n + c]; O[q] = cf((float)v.re, (float)v.im); }
+}
+
+bool coarse_invert_odd_self_fast(CoarseOp &op) {
+  const int n = op.n; const long nodd = op.V - op.n_even;
+  const size_t smem = ((size_t)n * n + n) * sizeof(cd);
+  if (nodd <= 0 || smem > 200 * 1024) return false;
+  static size_t attr = 0;
+  if (smem > attr) { CUDA_CHECK(cudaFuncSetAttribute(k_invert_self, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  k_invert_self<<<(unsigned)nodd, 256, smem, g_stream>>>(op, op.n_even, nodd);
+  g_launch_count++;
+#ifdef DDA_DEBUG_SYNC
+  CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());
+#endif
+  return true;
+}
+
 int g_coarse_stages = 0;   // 0: default; 3 / 4: force the depth of the TMA ring (tuning knob, env DDA_COARSE_STAGES)
 
 bool coarse_apply_fast(const CoarseOp &op, cf *out, const cf *in, cf *Z) {

@@ -49,10 +49,15 @@ void coarse_apply(const CoarseOp &op, cf *out, const cf *in, SiteSel sel, int ho
   }, 128);
 }
 
+bool coarse_invert_odd_self_fast(CoarseOp &op);   // coarse_kernel.cu (sm_100a): one CTA per site, block in shared memory
+
 void coarse_invert_odd_self(CoarseOp &op) {
   const int n = op.n; const long nn = (long)n * n;
   long nodd = op.V - op.n_even;
   if (nodd <= 0) return;
+#ifndef DDA_HOST_EMU
+  if (coarse_invert_odd_self_fast(op)) return;
+#endif
   cd *scratch = dev_alloc<cd>(2 * nn * nodd);
   const cf *S = op.S; cf *Sinv = op.Sinv; long ne = op.n_even;
   launch_n(nodd, DLAMBDA(long o) {
