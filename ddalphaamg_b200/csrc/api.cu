@@ -18,6 +18,10 @@ struct ApiState {
   int bc = 1;
   bool initialised = false;
   std::vector<double> stage;     // host staging (lexicographic)
+  // struct-route setup policy (dd_alpha_amg_parameters.h:36-38, dd_alpha_amg_setup_status.h)
+  dd_alpha_amg_parameters amg = {};
+  bool have_amg = false;
+  int updates_since_setup = 0, updates_since_setup_update = 0;
 };
 ApiState *A = nullptr;
 
@@ -81,6 +85,11 @@ void init_common(dd_alpha_amg_par &p, bool from_struct) {
   params_finalize(s.p);
   A->conf_index_fct = p.conf_index_fct; A->vector_index_fct = p.vector_index_fct; A->global_time = p.global_time;
   A->bc = p.bc;
+  if (from_struct) {
+    // init.c:899-900: the counters start at their thresholds, so the first "if necessary" check runs a setup
+    A->amg = p.amg_params; A->have_amg = true;
+    A->updates_since_setup = p.amg_params.discard_setup_after; A->updates_since_setup_update = p.amg_params.update_setup_after;
+  }
   s.seed = 20261018ULL + 7919ULL * (unsigned long long)g_comm.rank;
   solver_alloc_fine(s);
   A->initialised = true;
@@ -170,6 +179,7 @@ double *dd_alpha_amg_get_clover_pointer(void) {
 }
 void dd_alpha_amg_fields_updated(void) {
   need_init("dd_alpha_amg_fields_updated");
+  A->updates_since_setup++; A->updates_since_setup_update++;      // dd_alpha_amg.c:182-185
   if (!A->s.h_gauge.empty()) { solver_sync_host_mirrors(A->s, true); A->s.conf_set = true; }
 }
 
@@ -189,6 +199,7 @@ void dd_alpha_amg_update_parameters(const struct dd_alpha_amg_parameters *ap) {
 void dd_alpha_amg_setup(int iterations, int *status) {
   need_init("dd_alpha_amg_setup");
   mg_setup(A->s, iterations);
+  A->updates_since_setup = 0; A->updates_since_setup_update = 0;  // init.c:277-278
   if (status) { status[0] = 1; status[1] = (int)A->s.coarse_iter_count; }
 }
 void dd_alpha_amg_setup_external_threading(int iterations, int *status, int core, int thread, void *bd, void (*bf)(void *, int)) {
@@ -198,6 +209,7 @@ void dd_alpha_amg_setup_external_threading(int iterations, int *status, int core
 void dd_alpha_amg_setup_update(int iterations, int *status) {
   need_init("dd_alpha_amg_setup_update");
   mg_setup_update(A->s, iterations);
+  A->updates_since_setup_update = 0;                               // init.c:366
   if (status) { status[0] = 1; status[1] = (int)A->s.coarse_iter_count; }
 }
 void dd_alpha_amg_setup_update_external_threading(int iterations, int *status, int core, int thread, void *bd, void (*bf)(void *, int)) {
@@ -302,6 +314,25 @@ void DDalphaAMG_update_parameters(const struct dd_alpha_amg_parameters *ap) { dd
 void DDalphaAMG_setup(int iterations, int *status) { dd_alpha_amg_setup(iterations, status); }
 double DDalphaAMG_solve(double *out, double *in, double tol, int *status) { return dd_alpha_amg_wilson_solve(out, in, tol, 1.0, 1.0, status); }
 void DDalphaAMG_finalize(void) { dd_alpha_amg_free(); }
+
+// ------------------------------------------------------------------------------------ setup policy / test-vector files
+int dda_setup_if_necessary(void) {
+  need_init("dda_setup_if_necessary");
+  Solver &s = A->s;
+  int did = 0, st[2];
+  if (A->have_amg) {
+    if (!s.setup_done || A->updates_since_setup >= A->amg.discard_setup_after) { dd_alpha_amg_setup(s.p.setup_iter[0], st); did = 2; }
+    else if (A->updates_since_setup_update >= A->amg.update_setup_after) { dd_alpha_amg_setup_update(A->amg.update_setup_iterations[0], st); did = 1; }
+  }
+  if (s.conf_set && s.p.m0 != s.m0_op) solver_shift_mass(s, s.p.m0);
+  return did;
+}
+void dda_write_test_vectors(const char *basename) { need_init("dda_write_test_vectors"); tv_write(A->s, basename); }
+void dda_read_test_vectors(const char *basename) {
+  need_init("dda_read_test_vectors");
+  tv_read(A->s, basename);
+  mg_resetup_from_test_vectors(A->s);
+}
 
 // ------------------------------------------------------------------------------------ operator-level entry points
 int dda_is_emulation(void) {
@@ -480,6 +511,42 @@ void dda_level_op(int op, int depth, float *out_lex, const float *in_lex, int ip
     } break;
     default: fprintf(stderr, "dda_level_op: unknown op %d\n", op); fatal("API misuse", __FILE__, __LINE__);
   }
+}
+
+int dda_level_apply_mrhs(int depth, float *out_lex, const float *in_lex, int reps, double *ms_out) {
+  Level &L = setup_level(depth, "dda_level_apply_mrhs");
+  DDA_ASSERT(depth >= 1);
+#ifdef DDA_HOST_EMU
+  (void)out_lex; (void)in_lex; (void)reps; (void)ms_out; (void)L;
+  return -1;
+#else
+  const int NR = 12;
+  const long vs = L.geo.valloc(), zs = L.geo.V * 4 * L.geo.nc, nloc = L.geo.vlen();
+  cf *vin = dev_alloc<cf>(NR * vs), *vout = dev_alloc<cf>(NR * vs), *Zs = dev_alloc<cf>(NR * zs);
+  for (int j = 0; j < NR; j++) {
+    level_upload(L, vin + j * vs, in_lex + 2 * j * nloc);
+    lv_halo(L, vin + j * vs);
+  }
+  int rc = coarse_apply_mrhs(L.cop, vout, vin, Zs, vs, zs) ? 0 : -1;
+  dev_sync();
+  if (rc == 0) {
+    for (int j = 0; j < NR; j++) level_download(L, out_lex + 2 * j * nloc, vout + j * vs);
+    if (reps > 0 && ms_out) {
+      cudaEvent_t e0, e1;
+      CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+      CUDA_CHECK(cudaEventRecord(e0, g_stream));
+      for (int r = 0; r < reps; r++) coarse_apply_mrhs(L.cop, vout, vin, Zs, vs, zs);
+      CUDA_CHECK(cudaEventRecord(e1, g_stream));
+      CUDA_CHECK(cudaEventSynchronize(e1));
+      float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+      CUDA_CHECK(cudaEventDestroy(e0)); CUDA_CHECK(cudaEventDestroy(e1));
+      *ms_out = (double)ms / reps;
+    }
+  }
+  dev_sync();
+  dev_free(vin); dev_free(vout); dev_free(Zs);
+  return rc;
+#endif
 }
 
 // device-resident timing of one hot-path operator: `reps` back-to-back applications, returns milliseconds per

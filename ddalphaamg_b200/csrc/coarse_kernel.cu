@@ -153,6 +153,12 @@ __global__ void k_coarse_combine(CoarseOp op, cf *__restrict__ out, const cf *__
   out[i] = acc;
 }
 
+void coarse_combine(const CoarseOp &op, cf *out, const cf *in, const cf *Z) {
+  const long total = op.V * op.n;
+  k_coarse_combine<<<(unsigned)((total + 127) / 128), 128, 0, g_stream>>>(op, out, in, Z, total);
+  g_launch_count++;
+}
+
 // -------------------------------------------------------------------------------------------------------------------
 // Fused SAP block solve on an intermediate level: ONE CTA per Schwarz block runs all block_iter minimal-residual steps
 //   Dr = D_block r ;  alpha = <Dr,r>/<Dr,Dr> ;  e += alpha r ;  r -= alpha Dr          and finally   x += e.

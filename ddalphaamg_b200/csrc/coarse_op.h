@@ -41,6 +41,9 @@ bool coarse_apply_fast(const CoarseOp &op, cf *out, const cf *in, cf *Z);
 bool coarse_sap_mr_fast(const CoarseOp &op, cf *x, const cf *r, const int *d_blocklist, int nblk, int bs, int biter,
                         const int *d_jobs, int njobs);
 
+// 12 right-hand sides at once on the tensor cores (sm_100a only; mrhs_kernel.cu): out_j = D_c in_j, vectors j at
+// in + j * vstride; Z: scratch of 12 x zstride complex (zstride >= 4 n V).  Ghost slabs of the inputs must be current.
+bool coarse_apply_mrhs(const CoarseOp &op, cf *out, const cf *in, cf *Z, long vstride, long zstride);
 // even-odd Schur complement of the coarsest operator as streaming kernels (sm_100a only; schur_kernel.cu); vectors are
 // full-lattice arrays in global even-odd order, Z: 4*n complex per site, `skip`: device flag (kernels return if set)
 bool schur_fast_supported(const CoarseOp &op);

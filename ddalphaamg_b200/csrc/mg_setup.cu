@@ -252,12 +252,22 @@ void mg_setup(Solver &s, int setup_iters) {
     mg_rebuild_coarse(s, d);
   }
   s.setup_done = true;
-  if (setup_iters > 0) {
+  if (setup_iters > 0 && p.interpolation == 4) {
+    // iterative_PRECISION_setup case 4 (setup_generic.c:111-118): the setup iterations are replaced by test vectors from files
+    tv_read(s, p.tv_file.c_str());
+    re_setup(s, 0);
+  } else if (setup_iters > 0) {
     set_kcycle_tol(s, p.coarse_tol);
     bootstrap(s, 0, setup_iters);
     set_kcycle_tol(s, p.kcycle_tol);
   }
   if (m_solve != s.m0_op) solver_shift_mass(s, m_solve);
+  dev_sync();
+}
+
+void mg_resetup_from_test_vectors(Solver &s) {
+  DDA_ASSERT(s.setup_done && s.nlev > 1);
+  re_setup(s, 0);
   dev_sync();
 }
 

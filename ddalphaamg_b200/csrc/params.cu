@@ -50,6 +50,13 @@ void params_from_ini(Params &p, const char *path) {
   // solver parameters first (odd_even / method influence the geometry derivation)
   ini.get_ints("mixed precision:", &p.mixed_precision, 1);
   if (p.num_levels == 1) p.interpolation = 0; else ini.get_ints("interpolation:", &p.interpolation, 1);
+  if (p.interpolation == 4) {   // read_testvector_io_data_if_necessary (init.c:904-912); one file per vector, "<name>.NN"
+    std::string tv;
+    ini.need(ini.find("test vector io file name:", tv), "test vector io file name:");
+    size_t a = tv.find_first_not_of(' ');
+    p.tv_file = a == std::string::npos ? "" : tv.substr(a);
+    while (!p.tv_file.empty() && (p.tv_file.back() == ' ' || p.tv_file.back() == '\r')) p.tv_file.pop_back();
+  }
   ini.get_ints("randomize test vectors:", &p.randomize, 1);
   ini.get_ints("coarse grid iterations:", &p.coarse_iter, 1);
   ini.get_ints("coarse grid restarts:", &p.coarse_restart, 1);

@@ -34,6 +34,7 @@ struct Params {
   double kcycle_tol = 1e-1;
   int rhs = 1;
   std::string conf_path;
+  std::string tv_file;       // "test vector io file name:" (interpolation: 4)
 };
 
 // parse the reference's "key: value" format; aborts (reference error0 convention) on a missing mandatory key

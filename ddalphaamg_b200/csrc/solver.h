@@ -107,6 +107,10 @@ void mg_setup(Solver &s, int setup_iters);
 void mg_setup_update(Solver &s, int setup_iters);
 void mg_rebuild_coarse(Solver &s, int depth);                  // Galerkin operator of level depth+1 (and below) from P
 void mg_free(Solver &s);
+void mg_resetup_from_test_vectors(Solver &s);                 // P and the coarse operators from the current test vectors
+// test-vector files in the reference's vector format (io.cu)
+void tv_write(Solver &s, const char *basename);
+void tv_read(Solver &s, const char *basename);
 void mg_preconditioner(Solver &s, cd *out, const cd *in);     // one V/K-cycle on the fine level, double in/out
 void mg_vcycle(Solver &s, int depth, cf *phi, const cf *eta, bool zero_guess);
 void mg_smoother(Solver &s, int depth, cf *phi, const cf *eta, int iters, bool zero_guess);

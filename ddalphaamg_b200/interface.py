@@ -84,7 +84,8 @@ EXPORTS = ["dd_alpha_amg_init", "dd_alpha_amg_init_external_threading", "dd_alph
            "DDalphaAMG_finalize",
            "dda_info", "dda_set_option", "dda_get_stat", "dda_reset_stats", "dda_apply_dw", "dda_get_operator",
            "dda_set_interpolation", "dda_get_interpolation", "dda_level_op", "dda_bench_op", "dda_upload_source",
-           "dda_solve_device", "dda_download_solution",
+           "dda_solve_device", "dda_download_solution", "dda_level_apply_mrhs", "dda_write_test_vectors", "dda_read_test_vectors",
+           "dda_setup_if_necessary",
            "dda_comm_unique_id", "dda_comm_init", "dda_comm_finalize", "dda_comm_rank", "dda_comm_size",
            "dda_comm_init_callbacks", "dda_is_emulation"]
 
@@ -144,6 +145,11 @@ def load_library(path=None):
     L.dda_solve_device.argtypes = [C.c_double, ip, dp]
     L.dda_solve_device.restype = C.c_double
     L.dda_download_solution.argtypes = [dp]
+    L.dda_write_test_vectors.argtypes = [C.c_char_p]
+    L.dda_read_test_vectors.argtypes = [C.c_char_p]
+    L.dda_setup_if_necessary.restype = C.c_int
+    L.dda_level_apply_mrhs.argtypes = [C.c_int, fp, fp, C.c_int, dp]
+    L.dda_level_apply_mrhs.restype = C.c_int
     L.dda_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     L.dda_comm_unique_id.restype = C.c_int
     L.dda_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int]
@@ -214,7 +220,8 @@ def _ip(a):
 def write_ini(path, lattice, block, levels=2, test_vectors=(20, 28), setup_iter=(4, 3), post_smooth=(2, 2),
               block_iter=(4, 4), m0=-0.5, csw=1.0, tol=1e-10, restart=50, max_restart=20, coarse_tol=5e-2,
               coarse_iter=100, coarse_restart=5, mixed_precision=1, anti_pbc=1, method=2, kcycle=1,
-              coarse_lattice=None, coarse_block=None, odd_even=1, local_lattice=None, ncycle=(1, 1), relax=(1.0, 1.0)):
+              coarse_lattice=None, coarse_block=None, odd_even=1, local_lattice=None, ncycle=(1, 1), relax=(1.0, 1.0),
+              interpolation=2, tv_file=None):
     """Parameter file in the reference's "key: value" format (keys: src/init.c:592-962, sample.ini)."""
     loc = local_lattice or lattice
     lines = ["configuration: none", "format: 0", "right hand side: 0",
@@ -241,7 +248,9 @@ def write_ini(path, lattice, block, levels=2, test_vectors=(20, 28), setup_iter=
               "coarse grid restarts: %d" % coarse_restart, "print mode: 0", "method: %d" % method,
               "mixed precision: %d" % mixed_precision, "randomize test vectors: 0",
               "odd even preconditioning: %d" % odd_even, "kcycle: %d" % kcycle, "kcycle length: 5",
-              "kcycle restarts: 2", "kcycle tolerance: 1E-1", "interpolation: 2"]
+              "kcycle restarts: 2", "kcycle tolerance: 1E-1", "interpolation: %d" % interpolation]
+    if tv_file is not None:
+        lines += ["test vector io from single file: 0", "test vector io file name: %s" % tv_file]
     with open(path, "w") as f:
         f.write("\n".join(lines) + "\n")
     return path
@@ -534,6 +543,26 @@ class DDalphaAMG:
     def coarsest_solve(self, b):
         d = self.info(INFO.NUM_LEVELS) - 1
         return self._level_op(OP.COARSEST_SOLVE, d, b, d)
+
+    def write_test_vectors(self, basename):
+        self.L.dda_write_test_vectors(basename.encode())
+
+    def read_test_vectors(self, basename):
+        self.L.dda_read_test_vectors(basename.encode())
+
+    def setup_if_necessary(self):
+        return self.L.dda_setup_if_necessary()
+
+    def level_apply_mrhs(self, depth, vs, reps=0):
+        """12 right-hand sides at once on the tensor cores: vs [12][sites * site vars] -> (D_c vs[j])_j, ms per application."""
+        vs = np.ascontiguousarray(vs, dtype=np.complex64)
+        assert vs.shape[0] == 12
+        out = np.zeros_like(vs)
+        ms = np.zeros(1)
+        rc = self.L.dda_level_apply_mrhs(depth, _fp(out), _fp(vs), int(reps), _dp(ms))
+        if rc != 0:
+            raise RuntimeError("dda_level_apply_mrhs: level %d not supported" % depth)
+        return out, float(ms[0])
 
     def bench_op(self, op, depth=0, reps=10):
         return self.L.dda_bench_op(op, depth, reps)

@@ -60,6 +60,24 @@ void dda_get_interpolation(int depth, float *P_lex);
  *  DDA_OP_COARSEST_SOLVE out = approximate D_c^-1 in     coarse_solve_odd_even_PRECISION (coarse_oddeven_generic.c:1139) */
 void dda_level_op(int op, int depth, float *out_lex, const float *in_lex, int iparam, int flag);
 
+/* 12 right-hand sides at once: out[j] = D_c in[j], j < 12, on a coarse level (depth >= 1) through the tensor-core kernel
+ * (tcgen05.mma, TF32 x 3 split = fp32 accuracy).  Host arrays [12][sites * site vars] complex float, lexicographic.
+ * No reference counterpart; per column it equals DDA_OP_APPLY.  Returns 0, or -1 when the level's
+ * shape is not supported.  reps > 0: returns in *ms_out the device time per 12-RHS application over `reps` repetitions. */
+int dda_level_apply_mrhs(int depth, float *out_lex, const float *in_lex, int reps, double *ms_out);
+
+/* fine-level test vectors as files "<basename>.NN" in the reference's vector format (vector_io, io.c:704-845: global
+ * lexicographic sites, 12 complex doubles each; an optional <header> block is skipped on reading).  The reference reads
+ * the same files with "interpolation: 4" + "test vector io file name:" (setup_generic.c:131-162), and so does this
+ * library's parameter-file route.  dda_read_test_vectors also rebuilds P and the coarse operators (re_setup). */
+void dda_write_test_vectors(const char *basename);
+void dda_read_test_vectors(const char *basename);
+/* setup policy of the struct route (run_dd_alpha_amg_setup_if_necessary, dd_alpha_amg.c:85-93): full setup when
+ * discard_setup_after gauge updates have passed since the last setup, setup update after update_setup_after, then the mass
+ * of dd_alpha_amg_update_parameters.  The reference defines this routine but never calls it; it is offered here for
+ * HMC callers and does nothing unless called.  Returns 2 (setup), 1 (setup update) or 0. */
+int dda_setup_if_necessary(void);
+
 /* device-resident timing (CUDA events on the launching stream), milliseconds per application */
 double dda_bench_op(int op, int depth, int reps);
 /* device-resident solve: upload once, solve (timed on the device), download */

@@ -76,7 +76,8 @@ def _ip(a):
 def write_ini(path, lattice, block, levels=2, test_vectors=(20, 28), setup_iter=(4, 3), post_smooth=(2, 2),
               block_iter=(4, 4), m0=-0.5, csw=1.0, tol=1e-10, restart=50, max_restart=20, coarse_tol=5e-2,
               coarse_iter=100, coarse_restart=5, mixed_precision=1, anti_pbc=1, method=2, kcycle=1,
-              coarse_lattice=None, coarse_block=None, nthreads=1, local_lattice=None, odd_even=1, ncycle=(1, 1), relax=(1.0, 1.0)):
+              coarse_lattice=None, coarse_block=None, nthreads=1, local_lattice=None, odd_even=1, ncycle=(1, 1), relax=(1.0, 1.0),
+              interpolation=2, tv_file=None):
     """Writes a .ini in the reference's key:value format (keys: src/init.c:592-962)."""
     loc = local_lattice or lattice
     lines = ["configuration: none", "format: 0", "right hand side: 0",
@@ -102,7 +103,9 @@ def write_ini(path, lattice, block, levels=2, test_vectors=(20, 28), setup_iter=
               "coarse grid restarts: %d" % coarse_restart, "print mode: 1", "method: %d" % method,
               "mixed precision: %d" % mixed_precision, "randomize test vectors: 0",
               "odd even preconditioning: %d" % odd_even, "kcycle: %d" % kcycle, "kcycle length: 5",
-              "kcycle restarts: 2", "kcycle tolerance: 1E-1", "interpolation: 2"]
+              "kcycle restarts: 2", "kcycle tolerance: 1E-1", "interpolation: %d" % interpolation]
+    if tv_file is not None:
+        lines += ["test vector io from single file: 0", "test vector io file name: %s" % tv_file]
     with open(path, "w") as f:
         f.write("\n".join(lines) + "\n")
     return path
