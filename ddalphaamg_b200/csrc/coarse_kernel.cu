@@ -311,7 +311,7 @@ bool coarse_sap_mr_fast(const CoarseOp &op, cf *x, const cf *r, const int *d_blo
 // Gauss-Jordan without pivoting (the reference factorises LU without pivoting as well, coarse_oddeven_generic.c:24-73;
 // the explicit inverse replaces its forward / backward substitution, coarse_perform_fwd_bwd_subs :75-121).
 __global__ void __launch_bounds__(256) k_invert_self(CoarseOp op, long n_first, long nsites) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = op.n; const long nn = (long)n * n;
   cd *A = reinterpret_cast<cd *>(smem_raw);                       // row-major [n][n]
   cd *colp = A + nn;                                              // column p of the current step

@@ -50,5 +50,10 @@ bool schur_fast_supported(const CoarseOp &op);
 void schur_hop(const CoarseOp &op, int phase, const cf *in, const cf *self, cf *dir, cf *Z, const int *skip);
 void schur_mid(const CoarseOp &op, const cf *eta, const cf *dir, const cf *Z, cf *out, float a, float b, float cS, const int *skip);
 void schur_fin(const CoarseOp &op, const cf *eta, const cf *dir, const cf *Z, cf *out, float a, float b, const int *skip);
+// fused Arnoldi-step kernels of the coarsest-level GMRES (see dev_gmres.h): last Schur stage + inner products with the
+// basis; orthogonalisation + norm + Givens step by the last CTA
+struct GmresOff;
+void schur_fin_dots(const CoarseOp &op, const cf *dir, const cf *Z, cf *w, const cf *V, long stride, int j, double *hb, const int *skip);
+void gmres_axpy_givens(cf *w, const cf *V, long stride, int j, long nelem, double *S, int *ct, const GmresOff &o, double tol, unsigned *counter);
 
 }  // namespace dda

@@ -90,6 +90,29 @@ void coarsest_alloc(Solver &s) {
     C.dg.alloc(nsolve, p.coarse_iter, p.coarse_restart, p.coarse_tol, na);
     if (p.odd_even) C.dg.op = [sp](cf *out, const cf *in, const int *skip) { mg_coarsest_schur(*sp, out, in, skip); };
     else C.dg.op = [sp](cf *out, const cf *in, const int *) { mg_apply_op(*sp, sp->nlev - 1, out, in); };
+#ifndef DDA_HOST_EMU
+    bool fused = C.fast;
+    { const char *e = getenv("DDA_GMRES_FUSED"); if (e && atoi(e) == 0) fused = false; }
+    if (fused) {
+      // Arnoldi step = 5 launches: the three streaming Schur kernels, the last Schur stage fused with the inner products,
+      // orthogonalisation + norm + Givens (last CTA) -- instead of 10 with the generic reductions
+      C.counter = dev_alloc<unsigned>(1);
+      dev_zero(C.counter, sizeof(unsigned));
+      C.dg.op_dots = [sp](cf *w, const cf *vj, int j) {
+        Coarsest &K = sp->cst;
+        const CoarseOp &o_ = *K.op; const int *skip = K.dg.ctrl;
+        schur_hop(o_, 0, vj, nullptr, K.dir, K.Z, skip);
+        schur_mid(o_, nullptr, K.dir, K.Z, K.t[1], 0.f, 1.f, -1.f, skip);
+        schur_hop(o_, 1, K.t[1], vj, K.dir, K.Z, skip);
+        schur_fin_dots(o_, K.dir, K.Z, w, K.dg.V, K.dg.stride, j, K.dg.st + gmres_offsets(K.dg.m).HB, skip);
+      };
+      C.dg.fused_gate = [sp]() { return sp->use_fast != 0; };
+      C.dg.axpy_givens = [sp](int j) {
+        Coarsest &K = sp->cst;
+        gmres_axpy_givens(K.dg.w, K.dg.V, K.dg.stride, j, K.dg.n, K.dg.st, K.dg.ctrl, gmres_offsets(K.dg.m), K.dg.tol, K.counter);
+      };
+    }
+#endif
   }
   C.active = true;
 }
@@ -99,7 +122,8 @@ void coarsest_free(Solver &s) {
   if (!C.active) return;
   dev_free(C.b); dev_free(C.x); C.b = C.x = nullptr;
   for (int i = 0; i < 4; i++) { dev_free(C.t[i]); C.t[i] = nullptr; }
-  dev_free(C.dir); dev_free(C.Z); dev_free(C.gbuf); dev_free(C.d_src); dev_free(C.d_own);
+  dev_free(C.dir); dev_free(C.Z); dev_free(C.gbuf); dev_free(C.d_src); dev_free(C.d_own); dev_free(C.counter); C.counter = nullptr;
+  C.dg.op_dots = nullptr; C.dg.axpy_givens = nullptr; C.dg.fused_gate = nullptr;
   C.dir = C.Z = C.gbuf = nullptr; C.d_src = C.d_own = nullptr;
   C.dg.release(); C.hostk.release();
   if (C.replicated) {

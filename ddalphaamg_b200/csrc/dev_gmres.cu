@@ -6,15 +6,9 @@
 namespace dda {
 
 namespace {
-struct Off { long H, G, C, S, Y, HB, N; int m; };
-Off offsets(int m) {
-  Off o; o.m = m;
-  o.H = 0; o.G = o.H + 2L * (m + 1) * m; o.C = o.G + 2L * (m + 1); o.S = o.C + 2L * m; o.Y = o.S + 2L * m;
-  o.HB = o.Y + 2L * m; o.N = o.HB + 2L * (m + 1);
-  return o;
-}
-// scalars behind the norm slot: st[o.N] = ||.||^2 of the last norm reduction
-enum { SC_INVSCALE = 1, SC_NORM_R0 = 2, SC_RELRES = 3, SC_TOTAL = 8 };
+typedef GmresOff Off;
+inline Off offsets(int m) { return gmres_offsets(m); }
+enum { SC_INVSCALE = GM_INVSCALE, SC_NORM_R0 = GM_NORM_R0, SC_RELRES = GM_RELRES, SC_TOTAL = GM_SCALARS };
 
 HD cd ldc2(const double *p) { return cd(p[0], p[1]); }
 HD void stc2(double *p, cd v) { p[0] = v.re; p[1] = v.im; }
@@ -62,12 +56,18 @@ int DevGmres::solve(cf *x, const cf *b) {
       ct[0] = 0; ct[2] = 0; ct[3] = 0;
       if (g0 == 0.0) { ct[0] = 1; ct[3] = 1; S[o.N + SC_RELRES] = 0.0; S[o.N + SC_INVSCALE] = 0.0; }
       else S[o.N + SC_INVSCALE] = 1.0 / g0;
+      for (int i = 0; i < 2 * (o.m + 1); i++) S[o.HB + i] = 0.0;      // the fused step kernels accumulate into these
+      S[o.N] = 0.0;
     });
     launch_n(nn, DLAMBDA(long i) { const float f = (float)S[o.N + SC_INVSCALE]; Vb[i] = f * ww[i]; });
     int next_poll = std::min(m, std::max(1, predicted));
     bool done = false;
     for (int j = 0; j < m && !done; j++) {
       const cf *vj = Vb + (long)j * sd;
+      if (op_dots && axpy_givens && (!fused_gate || fused_gate())) {
+        op_dots(ww, vj, j);
+        axpy_givens(j);
+      } else {
       op(ww, vj, ct);
       // hbuf[k] = <V_k, w>, k <= j   (process_multi_inner_product, linalg_generic.c:107-154)
       launch_reduce<2>(j + 1, nn, DLAMBDA(long seg, long i, double *acc) {
@@ -86,35 +86,8 @@ int DevGmres::solve(cf *x, const cf *b) {
       }, S + o.N);
       comm_allreduce_sum(S + o.N, 1);
       // Hessenberg column, Givens rotations, convergence test (qr_update, linsolve_generic.c:898-940)
-      launch_n(1, DLAMBDA(long) {
-        if (ct[0]) return;
-        const int M1 = o.m + 1;
-        double *H = S + o.H + 2L * j * M1;            // column j
-        for (int i = 0; i <= j; i++) { H[2 * i] = S[o.HB + 2 * i]; H[2 * i + 1] = S[o.HB + 2 * i + 1]; }
-        const double hn = sqrt(S[o.N]);
-        H[2 * (j + 1)] = hn; H[2 * (j + 1) + 1] = 0.0;
-        ct[1] += 1; ct[2] = j + 1;
-        S[o.N + SC_INVSCALE] = hn > 1e-15 ? 1.0 / hn : 0.0;
-        if (hn > tl / 10) {
-          for (int i = 0; i < j; i++) {
-            const cd ci = ldc2(S + o.C + 2 * i), si = ldc2(S + o.S + 2 * i), h0 = ldc2(H + 2 * i), h1 = ldc2(H + 2 * i + 2);
-            const cd beta = (-si) * h0 + ci * h1;
-            stc2(H + 2 * i, conj(ci) * h0 + conj(si) * h1);
-            stc2(H + 2 * i + 2, beta);
-          }
-          const cd hj = ldc2(H + 2 * j), hj1 = ldc2(H + 2 * j + 2);
-          const double bn = sqrt(norm2(hj) + norm2(hj1));
-          const cd sj(hj1.re / bn, hj1.im / bn), cj(hj.re / bn, hj.im / bn);
-          stc2(S + o.S + 2 * j, sj); stc2(S + o.C + 2 * j, cj);
-          const cd gj = ldc2(S + o.G + 2 * j);
-          const cd gj1 = (-sj) * gj;
-          stc2(S + o.G + 2 * (j + 1), gj1); stc2(S + o.G + 2 * j, conj(cj) * gj);
-          stc2(H + 2 * j, cd(bn, 0.0)); stc2(H + 2 * j + 2, cd(0.0, 0.0));
-          const double rel = sqrt(norm2(gj1)) / S[o.N + SC_NORM_R0];
-          S[o.N + SC_RELRES] = rel;
-          if (rel < tl || rel > 1e5) { ct[0] = 1; ct[3] = 1; }
-        } else { ct[0] = 1; ct[3] = 1; }
-      });
+      launch_n(1, DLAMBDA(long) { gmres_givens(S, ct, o, j, tl); });
+      }
       if (j + 1 < m) {
         cf *vn = Vb + (long)(j + 1) * sd;
         launch_n(nn, DLAMBDA(long i) { if (ct[0]) return; const float f = (float)S[o.N + SC_INVSCALE]; vn[i] = f * ww[i]; });
@@ -145,8 +118,7 @@ int DevGmres::solve(cf *x, const cf *b) {
     });
     if (hc[3]) break;
   }
-  double rel = 0; d2h(&rel, S + o.N + SC_RELRES, sizeof(double));
-  last_relres = rel; last_iter = hc[1];
+  last_iter = hc[1];
   if (first_cycle_iters > 0) predicted = std::min(m, std::max(4, first_cycle_iters));
   return hc[1];
 }

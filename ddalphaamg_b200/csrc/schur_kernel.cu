@@ -20,6 +20,7 @@
 // (steps enqueued past convergence by the device-resident GMRES, dev_gmres.h).
 // Algorithmic traffic of one Schur application: 2 x (4 n^2) x V (every hop matrix twice) + n^2 x V (S_ee, Soo^-1), x 8 B.
 #include "coarse_op.h"
+#include "dev_gmres.h"
 #include "tma.cuh"
 
 namespace dda {
@@ -235,6 +236,86 @@ __global__ void k_schur_fin(CoarseOp op, const cf *__restrict__ eta, const cf *_
   out[i] = t;
 }
 
+// ---- fused Arnoldi-step kernels of the coarsest-level GMRES (dev_gmres.h hooks) ---------------------------------------
+// even sites: w(x) = dir(x) + sum_mu Z[x-mu][mu]  (the last stage of the Schur complement) AND the inner products
+// hb[2k], hb[2k+1] += <V_k, w> over the CTA's sites for k <= j: every warp takes basis vectors k = warp, warp + 8, ...;
+// double accumulation, one double atomic per CTA and value (process_multi_inner_product, linalg_generic.c:107-154).
+__global__ void __launch_bounds__(256)
+k_schur_fin_dots(CoarseOp op, const cf *__restrict__ dir, const cf *__restrict__ Z, cf *__restrict__ w, const cf *__restrict__ V,
+                 long stride, int j, double *__restrict__ hb, int spc, const int *__restrict__ skip) {
+  if (skip && *skip) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cf *ws = reinterpret_cast<cf *>(smem_raw);
+  const int n = op.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long x0 = (long)blockIdx.x * spc;
+  const int nloc = (int)(((op.n_even - x0) < spc ? (op.n_even - x0) : spc) * n);
+  for (int e = tid; e < nloc; e += 256) {
+    const long x = x0 + e / n; const int c = e % n;
+    cf t = dir[x * n + c];
+#pragma unroll
+    for (int mu = 0; mu < 4; mu++) t += Z[((long)op.nb[(long)(4 + mu) * op.V + x] * 4 + mu) * n + c];
+    w[x * n + c] = t; ws[e] = t;
+  }
+  __syncthreads();
+  for (int k = warp; k <= j; k += 8) {
+    const cf *vk = V + (long)k * stride + x0 * n;
+    double ar = 0.0, ai = 0.0;
+    for (int e = lane; e < nloc; e += 32) {
+      const cf a = vk[e], b = ws[e];
+      ar += (double)a.re * b.re + (double)a.im * b.im;
+      ai += (double)a.re * b.im - (double)a.im * b.re;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ar += __shfl_xor_sync(0xffffffffu, ar, o); ai += __shfl_xor_sync(0xffffffffu, ai, o); }
+    if (lane == 0) { atomicAdd(hb + 2 * k, ar); atomicAdd(hb + 2 * k + 1, ai); }
+  }
+}
+
+// w -= sum_{k<=j} h_k V_k, ||w||^2 (double atomic per CTA); the LAST CTA to finish runs the Givens / convergence step of
+// the iteration and clears the accumulation buffers for the next one (vector_PRECISION_multi_saxpy + global_norm + qr_update,
+// linsolve_generic.c:859-940).  No CTA waits for another one.
+__global__ void __launch_bounds__(256)
+k_gmres_axpy_givens(cf *__restrict__ w, const cf *__restrict__ V, long stride, int j, long nelem, double *S, int *ct, GmresOff o,
+                    double tl, unsigned *counter) {
+  if (ct[0]) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cf *hs = reinterpret_cast<cf *>(smem_raw);
+  __shared__ double red[8];
+  __shared__ unsigned ticket;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int k = tid; k <= j; k += 256) hs[k] = cf((float)S[o.HB + 2 * k], (float)S[o.HB + 2 * k + 1]);
+  __syncthreads();
+  const long e = (long)blockIdx.x * 256 + tid;
+  double loc = 0.0;
+  if (e < nelem) {
+    cf v = w[e];
+    for (int k = 0; k <= j; k++) fms_(v, hs[k], V[(long)k * stride + e]);
+    w[e] = v;
+    loc = (double)v.re * v.re + (double)v.im * v.im;
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, s);
+  if (lane == 0) red[warp] = loc;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < 8; i++) tot += red[i];
+    atomicAdd(&S[o.N], tot);
+    __threadfence();
+    ticket = atomicAdd(counter, 1u);
+  }
+  __syncthreads();
+  if (ticket == gridDim.x - 1 && tid == 0) {
+    __threadfence();
+    const double nv = atomicAdd(&S[o.N], 0.0);        // the coherent total of every CTA's contribution
+    S[o.N] = nv;
+    gmres_givens(S, ct, o, j, tl);
+    for (int i = 0; i < 2 * (j + 2); i++) S[o.HB + i] = 0.0;
+    S[o.N] = 0.0;
+    *counter = 0u;
+  }
+}
+
 namespace {
 int pick_groups(int n) {
   int G = 128 / (n / 2);
@@ -295,6 +376,27 @@ void schur_mid(const CoarseOp &op, const cf *eta, const cf *dir, const cf *Z, cf
 void schur_fin(const CoarseOp &op, const cf *eta, const cf *dir, const cf *Z, cf *out, float a, float b, const int *skip) {
   const long total = op.n_even * op.n;
   k_schur_fin<<<(unsigned)((total + 127) / 128), 128, 0, g_stream>>>(op, eta, dir, Z, out, a, b, skip);
+  g_launch_count++;
+#ifdef DDA_DEBUG_SYNC
+  CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());
+#endif
+}
+
+void schur_fin_dots(const CoarseOp &op, const cf *dir, const cf *Z, cf *w, const cf *V, long stride, int j, double *hb, const int *skip) {
+  const int spc = 4;                                             // sites per CTA: 216 CTAs on the 8 x 6^3 lattice
+  const size_t smem = (size_t)spc * op.n * sizeof(cf);
+  const long grid = (op.n_even + spc - 1) / spc;
+  k_schur_fin_dots<<<(unsigned)grid, 256, smem, g_stream>>>(op, dir, Z, w, V, stride, j, hb, spc, skip);
+  g_launch_count++;
+#ifdef DDA_DEBUG_SYNC
+  CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());
+#endif
+}
+
+void gmres_axpy_givens(cf *w, const cf *V, long stride, int j, long nelem, double *S, int *ct, const GmresOff &o, double tol, unsigned *counter) {
+  const size_t smem = (size_t)(o.m + 1) * sizeof(cf);
+  DDA_ASSERT(smem <= 40 * 1024);
+  k_gmres_axpy_givens<<<(unsigned)((nelem + 255) / 256), 256, smem, g_stream>>>(w, V, stride, j, nelem, S, ct, o, tol, counter);
   g_launch_count++;
 #ifdef DDA_DEBUG_SYNC
   CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());

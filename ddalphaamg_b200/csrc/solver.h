@@ -53,6 +53,7 @@ struct Coarsest {
   cf *t[4] = {};                          // work vectors (full lattice + ghosts)
   cf *dir = nullptr, *Z = nullptr;        // scratch of the scatter-form Schur kernels
   cf *gbuf = nullptr;                     // all-gather staging of a vector (replicated)
+  unsigned *counter = nullptr;            // ticket of the fused orthogonalisation kernel (last CTA runs the Givens step)
   int *d_src = nullptr, *d_own = nullptr; // replicated: gather source of global site g; global site of local site k
   DevGmres dg;                            // device-resident GMRES (default)
   Fgmres<float> hostk;                    // host-driven GMRES (DDA_COARSEST_HOST=1: round-1 behaviour, for comparison)
