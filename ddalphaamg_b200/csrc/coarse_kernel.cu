@@ -288,17 +288,20 @@ bool coarse_sap_mr_fast(const CoarseOp &op, cf *x, const cf *r, const int *d_blo
   const size_t nn = (size_t)n * n, len = (size_t)bs * n;
   int teams = (nblk <= 2 * sms) ? 4 : 1;            // few blocks per rank: more threads per block instead of more blocks per SM
   if (const char *e = getenv("DDA_SAP_TEAMS")) { const int t = atoi(e); if (t == 1 || t == 4) teams = t; }   // test / tuning override
-  const size_t smem = (size_t)teams * 2 * nn * sizeof(cf) + 4 * len * sizeof(cf) + 64 * sizeof(float) + njobs * sizeof(SapJob) + 8 * sizeof(uint64_t);
+  static int stages = 0;                            // depth of the TMA ring (DDA_SAPMR_STAGES = 2 | 3; tuning knob)
+  if (!stages) { const char *e = getenv("DDA_SAPMR_STAGES"); stages = (e && atoi(e) == 3) ? 3 : 2; }
+  const size_t smem = (size_t)teams * stages * nn * sizeof(cf) + 4 * len * sizeof(cf) + 64 * sizeof(float) + njobs * sizeof(SapJob) + 16 * sizeof(uint64_t);
   if (smem > 200 * 1024) return false;
-  static size_t attr1 = 0, attr4 = 0;
   const SapJob *jb = reinterpret_cast<const SapJob *>(d_jobs);
-  if (teams == 4) {
-    if (smem > attr4) { CUDA_CHECK(cudaFuncSetAttribute(k_coarse_sap_mr<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr4 = smem; }
-    k_coarse_sap_mr<2, 4><<<nblk, 512, smem, g_stream>>>(op, x, r, d_blocklist, bs, biter, jb, njobs, G);
-  } else {
-    if (smem > attr1) { CUDA_CHECK(cudaFuncSetAttribute(k_coarse_sap_mr<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr1 = smem; }
-    k_coarse_sap_mr<2, 1><<<nblk, 128, smem, g_stream>>>(op, x, r, d_blocklist, bs, biter, jb, njobs, G);
-  }
+  static size_t attr[4] = {0, 0, 0, 0};             // per kernel variant
+  auto go = [&](auto kern, int threads, int variant) {
+    if (smem > attr[variant]) { CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[variant] = smem; }
+    kern<<<nblk, threads, smem, g_stream>>>(op, x, r, d_blocklist, bs, biter, jb, njobs, G);
+  };
+  if (teams == 4 && stages == 2) go(k_coarse_sap_mr<2, 4>, 512, 0);
+  else if (teams == 4) go(k_coarse_sap_mr<3, 4>, 512, 1);
+  else if (stages == 2) go(k_coarse_sap_mr<2, 1>, 128, 2);
+  else go(k_coarse_sap_mr<3, 1>, 128, 3);
   g_launch_count++;
 #ifdef DDA_DEBUG_SYNC
   CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());

@@ -187,6 +187,9 @@ void Geometry::build() {
       tab[5 * l] = in; tab[5 * l + 1] = nf; tab[5 * l + 2] = nbk; tab[5 * l + 3] = lf; tab[5 * l + 4] = lb;
     }
     d_saptab = dev_upload(tab);
+    std::vector<int> slotsite(4 * 192, 0);
+    for (int l = 0; l < 256; l++) for (int m = 0; m < 4; m++) if (slot[m][l] < 192) slotsite[m * 192 + slot[m][l]] = l;
+    d_sapslotsite = dev_upload(slotsite);
   }
   // sites / blocks on the rank boundary (used to overlap the halo exchange with interior work)
   {
@@ -217,6 +220,7 @@ void Geometry::destroy() {
   dev_free(d_nbg); d_nbg = nullptr;
   dev_free(d_sapjobs); d_sapjobs = nullptr; nsapjobs = 0;
   dev_free(d_saptab); d_saptab = nullptr;
+  dev_free(d_sapslotsite); d_sapslotsite = nullptr;
   for (int c = 0; c < 2; c++) { dev_free(d_blocklist_int[c]); dev_free(d_blocklist_bnd[c]); d_blocklist_int[c] = d_blocklist_bnd[c] = nullptr; }
   d_nb = nullptr; d_blkflag = d_aggflag = nullptr; d_lex2nat = d_nat2lex = nullptr;
   d_blocklist[0] = d_blocklist[1] = nullptr; d_agg2coarse = nullptr;

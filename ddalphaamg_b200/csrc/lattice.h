@@ -53,6 +53,7 @@ struct Geometry {
   std::vector<int> lex2nat, nat2lex, block_color;
   std::vector<int> h_nb;     // [8][V]
   std::vector<unsigned char> h_blkflag;   // [V]
+  int *d_sapslotsite = nullptr;                 // [4][192]: block-local site of link slot (mu, slot)
   unsigned *d_saptab = nullptr;                 // fine level, 4^4 even-odd blocks: per block-local site {in-block mask, +mu / -mu
                                                 // neighbour index inside its parity, link slots} (fused SAP kernel v2)
   int *d_sapjobs = nullptr; int nsapjobs = 0;   // block operator as a job list {type, i, j, 0}: type 0 = self coupling of

@@ -417,7 +417,7 @@ struct Shared2 {
   float2 U[4][9][192];              // in-block links: [mu][3*row+col][slot of the link's source site]
   float2 Vb[12][BS / 2];            // exchange buffer [component][site of ONE parity]
   float red[2][BS / 32][4];
-  unsigned long long bar;
+  unsigned long long bar, barU;
 };
 
 struct Site2 {                      // one of the thread pair's two sites; packed bytes, one per direction
@@ -520,8 +520,8 @@ __device__ __forceinline__ void store_own(cf *v, long base, const Ctx &cx_, cons
 
 // tab: per block-local site 5 words {in, nf, nb, lf, lb} (identical for every block, built on the host)
 __global__ void __launch_bounds__(BS, 2)
-k_sap_fine2(FineOp<float> op, cf *x, const cf *__restrict__ eta, const int *__restrict__ blocklist, const unsigned *__restrict__ tab,
-            int biter, int first_zero) {
+k_sap_fine2(FineOp<float> op, const cf *__restrict__ Dblk, cf *x, const cf *__restrict__ eta, const int *__restrict__ blocklist,
+            const unsigned *__restrict__ tab, int biter, int first_zero, int ext) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Shared2 &sm = *reinterpret_cast<Shared2 *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -541,25 +541,15 @@ k_sap_fine2(FineOp<float> op, cf *x, const cf *__restrict__ eta, const int *__re
     tma_bulk_g2s(sm.Cb, src, CB_BYTES, bar);
   };
   auto cwait = [&]() { mbar_wait(bar, cphase & 1); cphase++; };
+  uint64_t *barU = reinterpret_cast<uint64_t *>(&sm.barU);
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(bar, 1); mbar_init(barU, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     cload(first_zero ? srcCinvO : srcCe);
-  }
-
-  // in-block links of the block -> shared memory: thread tid copies the links of site tid (coalesced 256 B rows)
-  {
-    const float2 *D2 = reinterpret_cast<const float2 *>(op.D);
-    const long st = base + tid;
-    const long u = (st >> 5) * (36L << 5) + (st & 31);
-    const unsigned slots = __ldg(tab + 5 * tid + 3), inb = __ldg(tab + 5 * tid);
-#pragma unroll
-    for (int mu = 0; mu < 4; mu++)
-      if (inb & (1u << mu)) {
-        const int sl = (slots >> (8 * mu)) & 0xFF;
-#pragma unroll
-        for (int k = 0; k < 9; k++) sm.U[mu][k][sl] = __ldg(D2 + u + ((long)(9 * mu + k) << 5));
-      }
+    // the 768 in-block links of the block: one bulk copy of the per-block image (solver_refresh_float_op)
+    const uint32_t UB = (uint32_t)sizeof(sm.U);
+    mbar_expect_tx(barU, UB);
+    tma_bulk_g2s(&sm.U[0][0][0], Dblk + (base / BS) * (4 * 9 * 192), UB, barU);
   }
   Site2 E, O;
   E.l = 16 * w + (lane & 15); O.l = BS / 2 + E.l;
@@ -574,7 +564,8 @@ k_sap_fine2(FineOp<float> op, cf *x, const cf *__restrict__ eta, const int *__re
 
   cf rE[6], rO[6];
   load_own(eta, vE, cx_, rE); load_own(eta, vO, cx_, rO);
-  __syncthreads();                                                      // links and barrier initialisation visible
+  __syncthreads();                                                      // barrier initialisation visible
+  bool links_ready = false;
   if (!first_zero) {
     // r_e = eta_e - C_e x_e - (N x)_e ,  r'_o = eta_o - (N x)_o : couplings to neighbouring blocks from global memory,
     // in-block hops through the exchange buffer, one parity at a time
@@ -585,14 +576,19 @@ k_sap_fine2(FineOp<float> op, cf *x, const cf *__restrict__ eta, const int *__re
 #pragma unroll
     for (int c = 0; c < 6; c++) rE[c] -= y[c];
     put2(sm, cx_, E.l, xe);
-    gl_hops(op, cx_, sE, (~E.in) & 0xFFu, x, y);
+    if (!ext) {
+      // ext: `eta` already is eta - (couplings to neighbouring blocks) x, computed by a separate full-occupancy kernel --
+      // the dependent global loads of these hops are what a CTA of 8 warps hides worst (ncu: a third of the visit)
+      gl_hops(op, cx_, sE, (~E.in) & 0xFFu, x, y);
 #pragma unroll
-    for (int c = 0; c < 6; c++) rE[c] -= y[c];
-    gl_hops(op, cx_, sO, (~O.in) & 0xFFu, x, y);
+      for (int c = 0; c < 6; c++) rE[c] -= y[c];
+      gl_hops(op, cx_, sO, (~O.in) & 0xFFu, x, y);
 #pragma unroll
-    for (int c = 0; c < 6; c++) rO[c] -= y[c];
+      for (int c = 0; c < 6; c++) rO[c] -= y[c];
+    }
     __syncthreads();                                                    // x_e in the buffer; C_e consumed by everybody
     if (tid == 0) cload(srcCinvO);
+    mbar_wait(barU, 0); links_ready = true;
     sm_hops2(sm, cx_, O, y);                                            // N_oe x_e
 #pragma unroll
     for (int c = 0; c < 6; c++) rO[c] -= y[c];
@@ -655,6 +651,7 @@ k_sap_fine2(FineOp<float> op, cf *x, const cf *__restrict__ eta, const int *__re
     if (tid == 0 && k > 0) cload(srcCe);
     put2(sm, cx_, E.l, z);
     __syncthreads();
+    if (!links_ready) { mbar_wait(barU, 0); links_ready = true; }
     cf y[6];
     sm_hops2(sm, cx_, E, y);                                            // N_eo (e_o or a2_o)
     if (k == 0) {
@@ -715,10 +712,16 @@ void sap_fine_fast(Solver &s, cf *x, const cf *eta, int iters, bool zero_guess) 
     CUDA_CHECK(cudaFuncSetAttribute(sap::k_sap_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sap::Shared)));
     CUDA_CHECK(cudaFuncSetAttribute(sap::k_sap_fine2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sap::Shared2)));
   }
-  const bool v2 = version == 2 && g.d_saptab;
+  const bool v2 = version == 2 && g.d_saptab && L.Dblk;
+  static int split = -1;     // 1: couplings to neighbouring blocks of the block residual in a kernel of their own (default)
+  if (split < 0) { const char *e = getenv("DDA_SAP_SPLIT"); split = e ? atoi(e) : 1; }
+  cf *rext = L.w[0];
   auto launch = [&](const int *list, int nblk, int first) {
     if (nblk <= 0) return;
-    if (v2) sap::k_sap_fine2<<<nblk, sap::BS, sizeof(sap::Shared2), g_stream>>>(L.opf, x, eta, list, g.d_saptab, biter, first);
+    if (v2 && split && !first) {
+      fine_apply<float>(L.opf, rext, x, sel_blocks(list, nblk, g.bs, 0, g.bs), HOP_CROSSBLOCK, 0, SELF_NONE, OUT_ETA_MINUS, eta);
+      sap::k_sap_fine2<<<nblk, sap::BS, sizeof(sap::Shared2), g_stream>>>(L.opf, L.Dblk, x, rext, list, g.d_saptab, biter, 0, 1);
+    } else if (v2) sap::k_sap_fine2<<<nblk, sap::BS, sizeof(sap::Shared2), g_stream>>>(L.opf, L.Dblk, x, eta, list, g.d_saptab, biter, first, 0);
     else sap::k_sap_fine<<<nblk, sap::BS, sizeof(sap::Shared), g_stream>>>(L.opf, x, eta, list, biter, first);
     g_launch_count++;
   };

@@ -22,6 +22,8 @@ struct Level {
   // ---- fine level (depth 0) operator storage
   cd *Dd = nullptr; double *Cd = nullptr;                      // double operator (outer solver)
   cf *Df = nullptr; float *Cf = nullptr, *Cinvf = nullptr;     // float copy used inside the cycle
+  cf *Dblk = nullptr;                    // 4^4 even-odd blocks: per block the 768 in-block links [mu][3*row+col][slot], the
+                                         // shared-memory image of the fused SAP kernel (one TMA bulk copy per block visit)
   FineOp<double> opd; FineOp<float> opf;
   // ---- coarse levels (depth >= 1)
   CoarseOp cop;

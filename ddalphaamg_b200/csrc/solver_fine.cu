@@ -63,7 +63,7 @@ void solver_alloc_fine(Solver &s) {
 void solver_free_fine(Solver &s) {
   if (!s.fine_alloc) return;
   Level &L = s.lev[0];
-  dev_free(L.Dd); dev_free(L.Cd); dev_free(L.Df); dev_free(L.Cf); dev_free(L.Cinvf);
+  dev_free(L.Dd); dev_free(L.Cd); dev_free(L.Df); dev_free(L.Cf); dev_free(L.Cinvf); dev_free(L.Dblk); L.Dblk = nullptr;
   dev_free(s.lexbuf); dev_free(s.xb); dev_free(s.xx);
   L.Dd = nullptr; L.Cd = nullptr; L.Df = nullptr; L.Cf = L.Cinvf = nullptr; s.lexbuf = s.xb = s.xx = nullptr;
   L.geo.destroy();
@@ -90,6 +90,17 @@ void solver_refresh_float_op(Solver &s) {
   Level &L = s.lev[0];
   long V = L.geo.V;
   cast_links(L.Dd, L.Df, (V + L.geo.Vg) * 36);
+  if (L.geo.d_sapslotsite) {
+    // per-block image of the in-block links for the fused SAP kernel (layout of sap::Shared2::U)
+    if (!L.Dblk) L.Dblk = dev_alloc<cf>((long)L.geo.nblocks * 4 * 9 * 192);
+    const cf *Df = L.Df; cf *Db = L.Dblk; const int *ss = L.geo.d_sapslotsite;
+    launch_n((long)L.geo.nblocks * 4 * 9 * 192, DLAMBDA(long i) {
+      const long b = i / (4 * 9 * 192); const int r = (int)(i - b * (4 * 9 * 192));
+      const int mu = r / (9 * 192), k = (r / 192) % 9, sl = r % 192;
+      const long site = b * 256 + ss[mu * 192 + sl];
+      Db[i] = Df[(site >> 5) * (36L << 5) + ((long)(9 * mu + k) << 5) + (site & 31)];
+    });
+  }
   cast_reals(L.Cd, L.Cf, V * 72);
   double *tmp = dev_alloc<double>(V * 72);
   fine_invert_clover(L.geo, L.Cd, tmp);
