@@ -38,6 +38,16 @@ def main():
             out["interpolate_d%d" % d] = S.bench_op(BENCH.INTERPOLATE, d, args.reps)
             out["smoother_d%d" % d] = S.bench_op(BENCH.SMOOTHER, d, 5)
         out["coarsest_schur"] = S.bench_op(BENCH.COARSEST_SCHUR, nlev - 1, 50)
+    if os.environ.get("DDA_BENCH_MRHS", "0") != "0":
+        # 12 right-hand sides at once on the tensor cores: ms per 12-RHS application and the single-RHS time next to it
+        rng = np.random.default_rng(3)
+        for d in range(1, nlev):
+            V, nc = S.level_shape(d)
+            vs = (rng.standard_normal((12, V * nc)) + 1j * rng.standard_normal((12, V * nc))).astype(np.complex64)
+            o, ms = S.level_apply_mrhs(d, vs, reps=10)
+            one = S.level_apply(d, vs[5])
+            out["mrhs12_apply_d%d_ms" % d] = ms
+            out["mrhs12_apply_d%d_relerr_col5" % d] = float(np.linalg.norm(o[5] - one) / np.linalg.norm(one))
     b = np.ones(S.V * 12, dtype=np.complex128)
     S.solve_device(b)
     res, st, ms = S.solve_device(b)
