@@ -43,7 +43,7 @@ WORKLOADS = {
     "48^3x96-L3": dict(lattice=[96, 48, 48, 48], levels=3, test_vectors=(20, 28), setup_iter=(3, 2), m0=-0.35,
                        coarse_block=[3, 2, 2, 2],
                        config="configs[3]: 48^3x96 synthetic gauge field, 3-level AMG near-physical mass"),
-    "64^3x128-L3": dict(lattice=[128, 64, 64, 64], levels=3, test_vectors=(20, 28), setup_iter=(3, 2), m0=-0.35,
+    "64^3x128-L3": dict(lattice=[128, 64, 64, 64], levels=3, test_vectors=(20, 28), setup_iter=(3, 2), m0=-0.3,
                         coarse_block=[2, 2, 2, 2],
                         config="configs[4]: 64^3x128 synthetic gauge field, 3-level AMG (needs >= 4 GPUs; single RHS)"),
 }
@@ -517,6 +517,62 @@ def run_native(args, w, name):
                      "note": "arithmetic intensity 8.7 flop/B puts the kernel on the fp32-issue side of the ridge: both fractions are reported"},
             "note": "D_W and coarse-operator GB/s (the metric's named kernels) are in `operators`"}
 
+    # ---- north-star target configuration, driver visible: 64^3 x 128 on the full 8 x B200 box, with its own parity record
+    target = None
+    if world == 8 and name == DEFAULT_WORKLOAD and not args.no_target:
+        tw = dict(WORKLOADS["64^3x128-L3"])
+        tw["mixed_precision"] = w.get("mixed_precision", 2)
+        tlat = tw["lattice"]
+        tkw = solver_kwargs(tw)
+        tl_t, tl_z = tlat[0] // PT, tlat[1] // PZ
+        tlocal = [tl_t, tl_z] + tlat[2:]
+        tkw["local_lattice"] = tlocal
+        twork = None
+        if not args.no_parity:
+            if rank == 0:
+                twork = tempfile.mkdtemp(prefix="dda_parity_t_", dir=tempfile.gettempdir())
+            obj = [twork]
+            dist.broadcast_object_list(obj, src=0)
+            twork = obj[0]
+        U = random_gauge_field(tlat, seed=20261018, eps=0.3, t_range=(cT * tl_t, (cT + 1) * tl_t))
+        if PZ > 1:
+            U = np.ascontiguousarray(U[:, cZ * tl_z:(cZ + 1) * tl_z])
+        T_ = DDalphaAMG(tlat, [4, 4, 4, 4], **tkw)
+        tplaq = T_.set_conf(U)
+        if twork:
+            np.save(os.path.join(twork, "U_%d.npy" % rank), U)
+        del U
+        t0 = time.time()
+        T_.setup(tw["setup_iter"][0])
+        tsetup = time.time() - t0
+        tb = np.ones(int(np.prod(tlocal)) * 12, dtype=np.complex128)
+        for _ in range(2):
+            T_.solve_device(tb)
+        barrier()
+        tms = 0.0
+        for _ in range(3):
+            tres, tst, ms_ = T_.solve_device(tb)
+            tms += ms_
+        barrier()
+        tsec = rank_max(tms) / 3e3
+        te = time.time()
+        T_.solve(tb)
+        barrier()
+        te2e = rank_max(time.time() - te)
+        tpar = {"skipped": "--no-parity"}
+        if twork:
+            T_.solve_device(tb)
+            txs = T_.download_solution()
+            tpar = parity_check(T_, tw, tlat, (PT, PZ), rank, world, twork, txs, dist)
+            del txs
+            barrier()
+            if rank == 0:
+                shutil.rmtree(twork, ignore_errors=True)
+        T_.free()
+        target = {"workload": "64^3x128-L3", "detail": tw["config"], "value": tsec, "unit": "s", "e2e": te2e, "n_gpus": world,
+                  "local_lattice_TZYX": tlocal, "m0": tw["m0"], "iterations": [int(tst[0]), int(tst[1])], "residual": tres,
+                  "plaquette": tplaq, "setup_seconds_untimed": tsetup, "steps": 3, "parity": tpar}
+
     if world > 1:
         from ddalphaamg_b200.interface import comm_finalize
         comm_finalize()
@@ -537,6 +593,8 @@ def run_native(args, w, name):
            "e2e": {"value": e2e, "unit": "s", "h2d_bytes_per_step": n * 16 * world, "d2h_bytes_per_step": n * 16 * world},
            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "operators": ops, "parity": parity,
            "time_share_seconds_profiled_solve": share, "wall_seconds_timed_region": wall}
+    if target is not None:
+        out["target_64c128"] = target
 
     if rank == 0 and world == 1 and not args.no_cpu:
         # the reference runs in its own process (it aborts the process on any error, main.h:424-439)
@@ -574,8 +632,9 @@ def run_native(args, w, name):
             out["sample_pair"] = {"failed": repr(e)}
     if rank == 0:
         print(json.dumps(out))
-    if isinstance(parity, dict) and parity.get("ok") is False:
-        raise RuntimeError("parity against the reference operator failed: %s" % json.dumps(parity))
+    for par_ in (parity, (target or {}).get("parity")):
+        if isinstance(par_, dict) and par_.get("ok") is False:
+            raise RuntimeError("parity against the reference operator failed: %s" % json.dumps(par_))
 
 
 def main():
@@ -588,6 +647,7 @@ def main():
     ap.add_argument("--m0", type=float, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed reference-operator parity check")
+    ap.add_argument("--no-target", action="store_true", help="N = 8 only: skip the extra 64^3x128 target-configuration block")
     ap.add_argument("--grid", type=lambda v: tuple(int(q) for q in v.split("x")), default=None, help="process grid TxZ, e.g. 4x2")
     ap.add_argument("--parity-slab", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--mixed-precision", type=int, default=2, choices=[1, 2],

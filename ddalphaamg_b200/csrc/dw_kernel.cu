@@ -112,6 +112,50 @@ k_dw_full(const cx<T> *__restrict__ D, const T *__restrict__ C, const int *__res
   for (int c = 0; c < 12; c++) out[tile_s + ((long)c << 5) + lane] = r[c];
 }
 
+// out(s) = eta(s) - [hops of s that LEAVE its Schwarz block] in, for the sites of the listed blocks: the couplings to the
+// neighbouring blocks of the SAP block residual (block_PRECISION_boundary_op, schwarz_generic.c:743-856) as a kernel of its
+// own with full occupancy -- inside the fused block-solve kernel (8 warps per block, 2 blocks per SM) the dependent global
+// loads of these hops were a fifth of the visit (profiles/r2_ncu_full_k_sap_fine2_a.txt).
+template <class T, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 4)
+k_dw_outer(const cx<T> *__restrict__ D, const int *__restrict__ nb, const unsigned char *__restrict__ blkflag,
+           const cx<T> *__restrict__ in, const cx<T> *__restrict__ eta, cx<T> *__restrict__ out, long V,
+           const int *__restrict__ blocklist, long nsel, int bs) {
+  const long i0 = blockIdx.x * (long)BLOCK + threadIdx.x;
+  if (i0 >= nsel) return;
+  const long b = i0 / bs;
+  const long s = (long)blocklist[b] * bs + (i0 - b * bs);
+  const int lane = (int)(s & 31);
+  const long tile = s >> 5;
+  const long tile_s = tile * (12L << 5), tile_u = tile * (36L << 5);
+  const unsigned f = blkflag[s];
+  cx<T> r[12];
+#pragma unroll
+  for (int c = 0; c < 12; c++) r[c] = ldc(eta + tile_s + ((long)c << 5) + lane);
+  if (f & 0x01u) dw_hop_fwd<0>(D, in, tile_u, lane, (long)__ldg(nb + 0 * V + s), r);
+  if (f & 0x10u) dw_hop_bwd<0>(D, in, (long)__ldg(nb + 4 * V + s), r);
+  if (f & 0x02u) dw_hop_fwd<1>(D, in, tile_u, lane, (long)__ldg(nb + 1 * V + s), r);
+  if (f & 0x20u) dw_hop_bwd<1>(D, in, (long)__ldg(nb + 5 * V + s), r);
+  if (f & 0x04u) dw_hop_fwd<2>(D, in, tile_u, lane, (long)__ldg(nb + 2 * V + s), r);
+  if (f & 0x40u) dw_hop_bwd<2>(D, in, (long)__ldg(nb + 6 * V + s), r);
+  if (f & 0x08u) dw_hop_fwd<3>(D, in, tile_u, lane, (long)__ldg(nb + 3 * V + s), r);
+  if (f & 0x80u) dw_hop_bwd<3>(D, in, (long)__ldg(nb + 7 * V + s), r);
+#pragma unroll
+  for (int c = 0; c < 12; c++) out[tile_s + ((long)c << 5) + lane] = r[c];
+}
+
+void dw_outer_fast(const FineOp<float> &op, cf *out, const cf *in, const cf *eta, const int *blocklist, int nblk, int bs) {
+  DDA_ASSERT(op.sh == 5);
+  const long nsel = (long)nblk * bs;
+  if (nsel <= 0) return;
+  const int BLOCK = 128;
+  k_dw_outer<float, BLOCK><<<(unsigned)((nsel + BLOCK - 1) / BLOCK), BLOCK, 0, g_stream>>>(op.D, op.nb, op.blkflag, in, eta, out, op.V, blocklist, nsel, bs);
+  g_launch_count++;
+#ifdef DDA_DEBUG_SYNC
+  CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());
+#endif
+}
+
 template <class T, int MODE> static void dw_launch(const FineOp<T> &op, cx<T> *out, const cx<T> *in, const int *list, long nlist) {
   const int BLOCK = 128;
   const long nthreads = (MODE == 2) ? nlist : op.V;

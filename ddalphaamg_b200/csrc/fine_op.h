@@ -62,4 +62,7 @@ void reals_to_lex(const Geometry &geo, double *dst_lex, const double *src, int n
 // optimised full-lattice D_W apply (sm_100a; dw_kernel.cu).  Not available in the emulation build.
 template <class T> void dw_apply_fast(const FineOp<T> &op, cx<T> *out, const cx<T> *in, int mode = 0, const int *list = nullptr, long nlist = 0);
 
+// out = eta - (hops that leave the Schwarz block) in, on the sites of the listed blocks (sm_100a; dw_kernel.cu)
+void dw_outer_fast(const FineOp<float> &op, cx<float> *out, const cx<float> *in, const cx<float> *eta, const int *blocklist, int nblk, int bs);
+
 }  // namespace dda

@@ -719,7 +719,7 @@ void sap_fine_fast(Solver &s, cf *x, const cf *eta, int iters, bool zero_guess) 
   auto launch = [&](const int *list, int nblk, int first) {
     if (nblk <= 0) return;
     if (v2 && split && !first) {
-      fine_apply<float>(L.opf, rext, x, sel_blocks(list, nblk, g.bs, 0, g.bs), HOP_CROSSBLOCK, 0, SELF_NONE, OUT_ETA_MINUS, eta);
+      dw_outer_fast(L.opf, rext, x, eta, list, nblk, g.bs);
       sap::k_sap_fine2<<<nblk, sap::BS, sizeof(sap::Shared2), g_stream>>>(L.opf, L.Dblk, x, rext, list, g.d_saptab, biter, 0, 1);
     } else if (v2) sap::k_sap_fine2<<<nblk, sap::BS, sizeof(sap::Shared2), g_stream>>>(L.opf, L.Dblk, x, eta, list, g.d_saptab, biter, first, 0);
     else sap::k_sap_fine<<<nblk, sap::BS, sizeof(sap::Shared), g_stream>>>(L.opf, x, eta, list, biter, first);
