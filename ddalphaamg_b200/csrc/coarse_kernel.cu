@@ -174,7 +174,7 @@ struct SapJob { int type, i, j, pad; };        // type 0: self coupling of local
 // all teams add into the same Dr.  TEAMS = 4 when a rank has fewer blocks than SMs (strong-scaling limit), else 1.
 template <int STAGES, int TEAMS>
 __global__ void __launch_bounds__(128 * TEAMS)
-k_coarse_sap_mr(CoarseOp op, cf *__restrict__ x, const cf *__restrict__ rin, const int *__restrict__ blocklist, int bs,
+k_coarse_sap_mr(CoarseOp op, cf *__restrict__ x, const cf *__restrict__ rin, const int *__restrict__ blocklist, int nblk, int bs,
                 int biter, const SapJob *__restrict__ jobs, int njobs, int G) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = op.n, nn = n * n, nh = n / 2, P = n / 2, ch = n / G;
@@ -194,14 +194,13 @@ k_coarse_sap_mr(CoarseOp op, cf *__restrict__ x, const cf *__restrict__ rin, con
   const int grp = tid / P, p = tid - grp * P;
   const bool active = grp < G;
   const uint32_t bytes = (uint32_t)(nn * sizeof(cf));
-  const long base = (long)blocklist[blockIdx.x] * bs;
   const int myjobs = (njobs - team + TEAMS - 1) / TEAMS;        // jobs team, team + TEAMS, ... of every MR step
-  const int total = biter * myjobs;
+  // persistent over the listed blocks: CTA b handles blocks b, b + gridDim, ...  With the grid capped so that the block
+  // operators of the concurrently processed blocks fit in L2 (DDA_SAPMR_GRID), MR steps 2..biter stream from L2
+  const int my_blocks = (nblk - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int per_block = biter * myjobs;
+  const int total = per_block * my_blocks;
   for (int q = gtid; q < njobs; q += NT) sj[q] = jobs[q];
-  for (int q = gtid; q < len; q += NT) {
-    const cf v = rin[base * n + q];
-    rv[q] = v; rg[q] = ((q % n) < nh) ? v : -v; ev[q] = cf(0.f, 0.f); Dr[q] = cf(0.f, 0.f);
-  }
   if (gtid == 0) {
     for (int s = 0; s < STAGES * TEAMS; s++) mbar_init(&full0[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -211,8 +210,10 @@ k_coarse_sap_mr(CoarseOp op, cf *__restrict__ x, const cf *__restrict__ rin, con
     if (TEAMS == 1) __syncthreads();
     else asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
   };
-  auto issue = [&](int jj) {                                     // jj-th job of this team
-    const SapJob jb = sj[(jj % myjobs) * TEAMS + team];
+  auto issue = [&](int jj) {                                     // jj-th job of this team (running over all its blocks)
+    const int bi = jj / per_block;
+    const long base = (long)blocklist[blockIdx.x + bi * gridDim.x] * bs;
+    const SapJob jb = sj[((jj - bi * per_block) % myjobs) * TEAMS + team];
     const cf *src = (jb.type == 0) ? op.S + (base + jb.i) * nn : op.F + ((base + jb.i) * 4 + (jb.type - 1)) * nn;
     const int st = jj % STAGES;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -223,6 +224,13 @@ k_coarse_sap_mr(CoarseOp op, cf *__restrict__ x, const cf *__restrict__ rin, con
   const float sgc = (2 * p < nh) ? 1.f : -1.f;                  // gamma5 sign of the thread's daggered output columns
 
   int jj = 0;
+  for (int bi = 0; bi < my_blocks; bi++) {
+  const long base = (long)blocklist[blockIdx.x + bi * gridDim.x] * bs;
+  for (int q = gtid; q < len; q += NT) {
+    const cf v = rin[base * n + q];
+    rv[q] = v; rg[q] = ((q % n) < nh) ? v : -v; ev[q] = cf(0.f, 0.f); Dr[q] = cf(0.f, 0.f);
+  }
+  __syncthreads();
   for (int it = 0; it < biter; it++) {
     for (int q = 0; q < myjobs; q++, jj++) {
       const int st = jj % STAGES;
@@ -274,6 +282,8 @@ k_coarse_sap_mr(CoarseOp op, cf *__restrict__ x, const cf *__restrict__ rin, con
     __syncthreads();
   }
   for (int q = gtid; q < len; q += NT) x[base * n + q] += ev[q];
+  __syncthreads();                                               // block vectors are re-initialised by the next block
+  }
 }
 
 bool coarse_sap_mr_fast(const CoarseOp &op, cf *x, const cf *r, const int *d_blocklist, int nblk, int bs, int biter,
@@ -288,6 +298,9 @@ bool coarse_sap_mr_fast(const CoarseOp &op, cf *x, const cf *r, const int *d_blo
   const size_t nn = (size_t)n * n, len = (size_t)bs * n;
   int teams = (nblk <= 2 * sms) ? 4 : 1;            // few blocks per rank: more threads per block instead of more blocks per SM
   if (const char *e = getenv("DDA_SAP_TEAMS")) { const int t = atoi(e); if (t == 1 || t == 4) teams = t; }   // test / tuning override
+  static int gridcap = -1;                          // DDA_SAPMR_GRID: persistent CTAs, at most this many (0: one CTA per block)
+  if (gridcap < 0) { const char *e = getenv("DDA_SAPMR_GRID"); gridcap = e ? atoi(e) : 0; }
+  const int grid = (gridcap > 0 && gridcap < nblk) ? gridcap : nblk;
   static int stages = 0;                            // depth of the TMA ring (DDA_SAPMR_STAGES = 2 | 3; tuning knob)
   if (!stages) { const char *e = getenv("DDA_SAPMR_STAGES"); stages = (e && atoi(e) == 3) ? 3 : 2; }
   const size_t smem = (size_t)teams * stages * nn * sizeof(cf) + 4 * len * sizeof(cf) + 64 * sizeof(float) + njobs * sizeof(SapJob) + 16 * sizeof(uint64_t);
@@ -296,7 +309,7 @@ bool coarse_sap_mr_fast(const CoarseOp &op, cf *x, const cf *r, const int *d_blo
   static size_t attr[4] = {0, 0, 0, 0};             // per kernel variant
   auto go = [&](auto kern, int threads, int variant) {
     if (smem > attr[variant]) { CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[variant] = smem; }
-    kern<<<nblk, threads, smem, g_stream>>>(op, x, r, d_blocklist, bs, biter, jb, njobs, G);
+    kern<<<grid, threads, smem, g_stream>>>(op, x, r, d_blocklist, nblk, bs, biter, jb, njobs, G);
   };
   if (teams == 4 && stages == 2) go(k_coarse_sap_mr<2, 4>, 512, 0);
   else if (teams == 4) go(k_coarse_sap_mr<3, 4>, 512, 1);

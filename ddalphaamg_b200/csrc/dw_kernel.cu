@@ -129,9 +129,11 @@ k_dw_outer(const cx<T> *__restrict__ D, const int *__restrict__ nb, const unsign
   const long tile = s >> 5;
   const long tile_s = tile * (12L << 5), tile_u = tile * (36L << 5);
   const unsigned f = blkflag[s];
+  // the hop functions SUBTRACT (1 -+ gamma) U phi, i.e. they add the operator's off-diagonal part N phi; the residual needs
+  // eta - N phi, so the accumulation runs on -eta and the sign is flipped at the end
   cx<T> r[12];
 #pragma unroll
-  for (int c = 0; c < 12; c++) r[c] = ldc(eta + tile_s + ((long)c << 5) + lane);
+  for (int c = 0; c < 12; c++) r[c] = -ldc(eta + tile_s + ((long)c << 5) + lane);
   if (f & 0x01u) dw_hop_fwd<0>(D, in, tile_u, lane, (long)__ldg(nb + 0 * V + s), r);
   if (f & 0x10u) dw_hop_bwd<0>(D, in, (long)__ldg(nb + 4 * V + s), r);
   if (f & 0x02u) dw_hop_fwd<1>(D, in, tile_u, lane, (long)__ldg(nb + 1 * V + s), r);
@@ -141,7 +143,7 @@ k_dw_outer(const cx<T> *__restrict__ D, const int *__restrict__ nb, const unsign
   if (f & 0x08u) dw_hop_fwd<3>(D, in, tile_u, lane, (long)__ldg(nb + 3 * V + s), r);
   if (f & 0x80u) dw_hop_bwd<3>(D, in, (long)__ldg(nb + 7 * V + s), r);
 #pragma unroll
-  for (int c = 0; c < 12; c++) out[tile_s + ((long)c << 5) + lane] = r[c];
+  for (int c = 0; c < 12; c++) out[tile_s + ((long)c << 5) + lane] = -r[c];
 }
 
 void dw_outer_fast(const FineOp<float> &op, cf *out, const cf *in, const cf *eta, const int *blocklist, int nblk, int bs) {

@@ -14,9 +14,10 @@
 //     Re Y[r][j] = P[2r][j] - P[2r+1][12+j] ,  Im Y[r][j] = P[2r+1][j] + P[2r][12+j]                     (forward product)
 // and with B' = [w | -i w] laid out along rho (w = G5 V(x))
 //     Q = W^T B' :  Q[c][j] = sum_r Mr wr + Mi wi = Re (M^H w)_c ,  Q[c][12+j] = sum_r Mr wi - Mi wr = Im (M^H w)_c  (daggered)
-// Both products read the SAME shared-memory copy of the block: 16-byte chunks (4 consecutive rho of one column) grouped
-// by 8 consecutive columns into 128-byte core matrices -- the canonical no-swizzle operand layout of tcgen05.mma, which is
-// "MN-major A" (M = rho, K = c) for the forward product and "K-major A" (M = c, K = rho) for the daggered one.
+// Both products use K-major operands in the canonical no-swizzle layout of tcgen05.mma (128-byte core matrices of 8 rows x
+// 4 K-elements).  For the daggered product (M = column c, K = rho) that is the block as it lies in memory, 16-byte chunks
+// of 4 consecutive rho grouped by 8 columns; for the forward product (M = rho, K = c) the block is transposed while it is
+// re-tiled.
 // fp32 accuracy on TF32 hardware: every operand is split x = hi + lo (hi = 11 significant bits) and each product is three
 // MMAs hi*hi + lo*hi + hi*lo accumulated in the same fp32 TMEM accumulator (error ~2^-21 relative).
 //
@@ -99,19 +100,26 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
   lo = x - hi;
 }
 
-// Operand buffers (floats).  A: [8 column groups][32 rho groups][8 columns][4 rho] = 8192 floats (n <= 64).
-// B (forward): [4 row groups of 8 right-hand-side slots][n/4 K cores][8][4].  B' (daggered): same with K = 2n.
-const int A_FLOATS = 8 * 32 * 32;
+// Operand buffers (floats), all in the canonical no-swizzle K-major layout of tcgen05.mma (verified on the B200 with
+// scripts/umma_probe.cu: 128-byte core matrices = 8 rows x 4 K-elements, leading byte offset = distance of the cores
+// adjacent in K, stride byte offset = distance of the 8-row groups):
+//   Af: forward view,  M = rho (16 row groups), K = column c (n/4 cores per row group)      -- the block TRANSPOSED
+//   Ad: daggered view, M = column c (8 row groups of 32 cores), K = rho                     -- the block as it lies in memory
+//   Bf: [Re V | Im V], N = 32 right-hand-side slots (4 row groups), K = c;   Bd: [w | -i w], K = rho
+const int AD_FLOATS = 8 * 32 * 32;
 
 template <int STAGES>
 __global__ void __launch_bounds__(128)
 k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *__restrict__ Z, long vstride, long zstride, int nsites) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int n = op.n, nn = n * n, nh = n / 2, n2 = 2 * n;
-  const int kcf = n / 4, kcd = n2 / 4;                              // K cores of the forward / daggered B operand
-  float *Ahi = reinterpret_cast<float *>(smem_raw);
-  float *Alo = Ahi + A_FLOATS;
-  float *Bfh = Alo + A_FLOATS;                                      // [4][kcf][32]
+  const int kcf = n / 4, kcd = n2 / 4;                              // K cores of the forward / daggered operands
+  const int AF_FLOATS = 16 * kcf * 32;
+  float *Afh = reinterpret_cast<float *>(smem_raw);
+  float *Afl = Afh + AF_FLOATS;
+  float *Adh = Afl + AF_FLOATS;
+  float *Adl = Adh + AD_FLOATS;
+  float *Bfh = Adl + AD_FLOATS;                                     // [4][kcf][32]
   float *Bfl = Bfh + 4 * kcf * 32;
   float *Bdh = Bfl + 4 * kcf * 32;                                  // [4][kcd][32]
   float *Bdl = Bdh + 4 * kcd * 32;
@@ -119,12 +127,12 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
   uint64_t *full = reinterpret_cast<uint64_t *>(raw + (size_t)STAGES * nn);   // [STAGES]
   uint64_t *mma_done = full + STAGES;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mma_done + 1);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bytes = (uint32_t)(nn * sizeof(cf));
   const int my_sites = (nsites - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total = 5 * my_sites;
 
-  for (int q = tid; q < 2 * A_FLOATS + 8 * (kcf + kcd) * 32; q += 128) Ahi[q] = 0.f;   // padding rows / columns stay zero
+  for (int q = tid; q < 2 * AF_FLOATS + 2 * AD_FLOATS + 8 * (kcf + kcd) * 32; q += 128) Afh[q] = 0.f;   // padding stays zero
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
     mbar_init(mma_done, 1);
@@ -150,60 +158,86 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
   };
   if (tid == 0) for (int j = 0; j < STAGES && j < total; j++) issue(j);
 
-  const uint32_t idesc_f = instr_desc(1, 0, 128, NB);               // forward: A = W as MN-major (M = rho), B K-major
-  const uint32_t idesc_d = instr_desc(0, 0, 128, NB);               // daggered: A = W as K-major (M = column)
-  const uint32_t aAhi = smem_u32(Ahi), aAlo = smem_u32(Alo), aBfh = smem_u32(Bfh), aBfl = smem_u32(Bfl), aBdh = smem_u32(Bdh), aBdl = smem_u32(Bdl);
+  const uint32_t idesc = instr_desc(0, 0, 128, NB);                 // A and B K-major, D = 128 x 32 fp32
+  const uint32_t aAfh = smem_u32(Afh), aAfl = smem_u32(Afl), aAdh = smem_u32(Adh), aAdl = smem_u32(Adl);
+  const uint32_t aBfh = smem_u32(Bfh), aBfl = smem_u32(Bfl), aBdh = smem_u32(Bdh), aBdl = smem_u32(Bdl);
   uint32_t mma_phase = 0;
+
+  // the right-hand sides a block multiplies (12 x n complex) are fetched one block ahead into registers
+  const int NPRE = 6;                                               // 12 * 64 / 128
+  cf pre[NPRE];
+  auto prefetch = [&](int j) {                                      // vectors of block j: site x (S) or x + mu (F_mu)
+    const int k = j / 5, m = j - 5 * k;
+    const long x = (long)blockIdx.x + (long)k * gridDim.x;
+    const long src = (m == 0) ? x : (long)op.nb[(long)(m - 1) * op.V + x];
+#pragma unroll
+    for (int i = 0; i < NPRE; i++) {
+      const int q = tid + 128 * i;
+      if (q < NR * n) { const int jr = q / n, c = q - jr * n; pre[i] = in[(long)jr * vstride + src * n + c]; }
+    }
+  };
+  if (total > 0) prefetch(0);
 
   for (int k = 0; k < my_sites; k++) {
     const long x = (long)blockIdx.x + (long)k * gridDim.x;
-    // B' = [w | -i w] along rho, w = G5 V_j(x): rows j (Re part of the result) and 12 + j (Im part)
-    for (int q = tid; q < NR * n; q += 128) {
-      const int j = q / n, r = q - j * n;
-      cf w = in[(long)j * vstride + x * n + r];
-      if (r >= nh) w = -w;
-      const float val[2][2] = {{w.re, w.im}, {w.im, -w.re}};         // [row block][re|im position]
-#pragma unroll
-      for (int blk = 0; blk < 2; blk++) {
-        const int row = blk * NR + j;
-#pragma unroll
-        for (int ri = 0; ri < 2; ri++) {
-          const int kk = 2 * r + ri;
-          const int o = ((row >> 3) * kcd + (kk >> 2)) * 32 + (row & 7) * 4 + (kk & 3);
-          float hi, lo; split_tf32(val[blk][ri], hi, lo);
-          Bdh[o] = hi; Bdl[o] = lo;
-        }
-      }
-    }
     for (int m = 0; m < 5; m++) {
       const int j = 5 * k + m, st = j % STAGES;
-      // forward B = [Re V | Im V] of the site this block multiplies: x itself (S) or x + mu (F_mu)
-      {
-        const long src = (m == 0) ? x : (long)op.nb[(long)(m - 1) * op.V + x];
-        for (int q = tid; q < NR * n; q += 128) {
+      // forward B = [Re V | Im V] from the prefetched registers; for m = 0 these are the site's own vectors, from which
+      // the daggered operand B' = [w | -i w], w = G5 V(x), is filled as well (rows j and 12 + j, K = rho = 2 r + re|im)
+#pragma unroll
+      for (int i = 0; i < NPRE; i++) {
+        const int q = tid + 128 * i;
+        if (q < NR * n) {
           const int jr = q / n, c = q - jr * n;
-          const cf v = in[(long)jr * vstride + src * n + c];
-          const int o0 = ((jr >> 3) * kcf + (c >> 2)) * 32 + (jr & 7) * 4 + (c & 3);
+          const cf v = pre[i];
           const int row1 = NR + jr;
+          const int o0 = ((jr >> 3) * kcf + (c >> 2)) * 32 + (jr & 7) * 4 + (c & 3);
           const int o1 = ((row1 >> 3) * kcf + (c >> 2)) * 32 + (row1 & 7) * 4 + (c & 3);
           float hi, lo;
           split_tf32(v.re, hi, lo); Bfh[o0] = hi; Bfl[o0] = lo;
           split_tf32(v.im, hi, lo); Bfh[o1] = hi; Bfl[o1] = lo;
+          if (m == 0) {
+            const cf w = (c >= nh) ? -v : v;
+            const float val[2][2] = {{w.re, w.im}, {w.im, -w.re}};   // [row block][re | im position]
+#pragma unroll
+            for (int blk = 0; blk < 2; blk++) {
+              const int row = blk * NR + jr;
+#pragma unroll
+              for (int ri = 0; ri < 2; ri++) {
+                const int kk = 2 * c + ri;
+                const int o = ((row >> 3) * kcd + (kk >> 2)) * 32 + (row & 7) * 4 + (kk & 3);
+                split_tf32(val[blk][ri], hi, lo);
+                Bdh[o] = hi; Bdl[o] = lo;
+              }
+            }
+          }
         }
       }
+      if (j + 1 < total) prefetch(j + 1);
       mbar_wait_bounded(&full[st], (uint32_t)((j / STAGES) & 1));
-      // re-tile the raw block: chunk (column c, rho group g) -> core matrix (c / 8, g), row c % 8
+      // re-tile the raw block (column-major complex = real W[rho][c], rho fastest): 16-byte chunk (column c, rho = 4g..4g+3)
+      //   daggered view: core matrix (c / 8, g), row c % 8          (one 16-byte store)
+      //   forward view:  element (rho, c) -> core (rho / 8, c / 4), row rho % 8, position c % 4   (four scalar stores)
+      // lanes: c % 4 = lane % 4, g % 2 = (lane / 4) % 2 -> the scalar stores of one instruction hit 8 distinct banks
       {
         const float4 *R4 = reinterpret_cast<const float4 *>(raw + (size_t)st * nn);
-        const int chunks = n * kcd;
-        for (int q = tid; q < chunks; q += 128) {
-          const int g = q / n, c = q - g * n;                        // consecutive threads: consecutive columns
+        const int ncq = n >> 2, ngq = kcd >> 1, combos = ncq * ngq;
+        for (int u = warp * 4 + (lane >> 3); u < combos; u += 16) {
+          const int cq = u / ngq, gq = u - cq * ngq;
+          const int c = 4 * cq + (lane & 3), g = 2 * gq + ((lane >> 2) & 1);
           const float4 v = R4[c * kcd + g];
           float4 h, l;
           split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-          const int o = ((c >> 3) * 32 + g) * 32 + (c & 7) * 4;
-          *reinterpret_cast<float4 *>(Ahi + o) = h;
-          *reinterpret_cast<float4 *>(Alo + o) = l;
+          const int od = ((c >> 3) * 32 + g) * 32 + (c & 7) * 4;
+          *reinterpret_cast<float4 *>(Adh + od) = h;
+          *reinterpret_cast<float4 *>(Adl + od) = l;
+          const float hv[4] = {h.x, h.y, h.z, h.w}, lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            const int rho = 4 * g + t;
+            const int of = ((rho >> 3) * kcf + (c >> 2)) * 32 + (rho & 7) * 4 + (c & 3);
+            Afh[of] = hv[t]; Afl[of] = lv[t];
+          }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // operand buffers written by the generic proxy
@@ -211,25 +245,25 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
       __syncthreads();
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // forward: K = n (8 columns = one column group per step); A start advances by one column group (32 cores of 128 B)
+        // forward: D_fwd[rho][slot] += sum_c W[rho][c] B[slot][c]; K = n, 8 per MMA = two cores (256 B) of A and of B
         for (int ks = 0; ks < n / 8; ks++) {
-          const uint32_t ao = (uint32_t)ks * 32 * 128, bo = (uint32_t)ks * 256;
-          const uint64_t ah = smem_desc(aAhi + ao, 4096, 128), al = smem_desc(aAlo + ao, 4096, 128);
-          const uint64_t bh = smem_desc(aBfh + bo, 128, (uint32_t)kcf * 128), bl = smem_desc(aBfl + bo, 128, (uint32_t)kcf * 128);
-          mma_tf32(tmem, ah, bh, idesc_f, (m > 0 || ks > 0) ? 1u : 0u);
-          mma_tf32(tmem, al, bh, idesc_f, 1u);
-          mma_tf32(tmem, ah, bl, idesc_f, 1u);
+          const uint32_t o = (uint32_t)ks * 256;
+          const uint64_t ah = smem_desc(aAfh + o, 128, (uint32_t)kcf * 128), al = smem_desc(aAfl + o, 128, (uint32_t)kcf * 128);
+          const uint64_t bh = smem_desc(aBfh + o, 128, (uint32_t)kcf * 128), bl = smem_desc(aBfl + o, 128, (uint32_t)kcf * 128);
+          mma_tf32(tmem, ah, bh, idesc, (m > 0 || ks > 0) ? 1u : 0u);
+          mma_tf32(tmem, al, bh, idesc, 1u);
+          mma_tf32(tmem, ah, bl, idesc, 1u);
         }
         if (m > 0) {
-          // daggered: K = 2n (8 rho = two rho groups per step); A start advances by two cores
+          // daggered: D_mu[c][slot] = sum_rho W[rho][c] B'[slot][rho]; K = 2n
           const uint32_t td = tmem + 32u * (uint32_t)m;
           for (int ks = 0; ks < n2 / 8; ks++) {
-            const uint32_t ao = (uint32_t)ks * 256, bo = (uint32_t)ks * 256;
-            const uint64_t ah = smem_desc(aAhi + ao, 128, 4096), al = smem_desc(aAlo + ao, 128, 4096);
-            const uint64_t bh = smem_desc(aBdh + bo, 128, (uint32_t)kcd * 128), bl = smem_desc(aBdl + bo, 128, (uint32_t)kcd * 128);
-            mma_tf32(td, ah, bh, idesc_d, ks > 0 ? 1u : 0u);
-            mma_tf32(td, al, bh, idesc_d, 1u);
-            mma_tf32(td, ah, bl, idesc_d, 1u);
+            const uint32_t o = (uint32_t)ks * 256;
+            const uint64_t ah = smem_desc(aAdh + o, 128, 4096), al = smem_desc(aAdl + o, 128, 4096);
+            const uint64_t bh = smem_desc(aBdh + o, 128, (uint32_t)kcd * 128), bl = smem_desc(aBdl + o, 128, (uint32_t)kcd * 128);
+            mma_tf32(td, ah, bh, idesc, ks > 0 ? 1u : 0u);
+            mma_tf32(td, al, bh, idesc, 1u);
+            mma_tf32(td, ah, bl, idesc, 1u);
           }
         }
         mma_commit(mma_done);                                        // arrives when every MMA issued so far has completed
@@ -264,7 +298,7 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();                                                 // accumulators and B' are free for the next site
+    __syncthreads();                                                 // accumulators are free for the next site
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -283,8 +317,8 @@ bool coarse_apply_mrhs(const CoarseOp &op, cf *out, const cf *in, cf *Z, long vs
   if (n > 64 || n < 8 || (n & 7) || op.V <= 0) return false;
   const size_t nn = (size_t)n * n;
   const int STAGES = 2;
-  const size_t smem = (2 * (size_t)mrhs::A_FLOATS + 8 * (size_t)(n / 4 + n / 2) * 32) * sizeof(float) + STAGES * nn * sizeof(cf) +
-                      (STAGES + 1) * sizeof(uint64_t) + 16;
+  const size_t smem = (2 * (size_t)(16 * (n / 4) * 32) + 2 * (size_t)mrhs::AD_FLOATS + 8 * (size_t)(n / 4 + n / 2) * 32) * sizeof(float) +
+                      STAGES * nn * sizeof(cf) + (STAGES + 1) * sizeof(uint64_t) + 16;
   static size_t attr = 0;
   if (smem > attr) { CUDA_CHECK(cudaFuncSetAttribute(mrhs::k_coarse_mrhs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
   static int sms = 0;
