@@ -217,34 +217,46 @@ void dd_alpha_amg_setup_update_external_threading(int iterations, int *status, i
   if (core == 0) dd_alpha_amg_setup_update(iterations, status);
 }
 
+// offsets of the caller's vector layout, evaluated once (the callback is a per-site function call in the reference,
+// dd_alpha_amg.c:345-352, on every solve) and reused by all later solves
+static const std::vector<long> &vector_offsets() {
+  static std::vector<long> off;
+  static void *for_fct = nullptr; static long for_V = -1;
+  Level &L0 = A->s.lev[0];
+  const int *L = L0.geo.L; const long V = L0.geo.V;
+  if (for_fct != (void *)A->vector_index_fct || for_V != V) {
+    off.resize(V);
+    long j = 0;
+    for (int t = 0; t < L[0]; t++) for (int z = 0; z < L[1]; z++) for (int y = 0; y < L[2]; y++) for (int x = 0; x < L[3]; x++)
+      off[j++] = A->vector_index_fct(t, z, y, x);
+    for_fct = (void *)A->vector_index_fct; for_V = V;
+  }
+  return off;
+}
 static void gather_source(const double *in, cd *dev_native) {
   Solver &s = A->s; Level &L0 = s.lev[0];
-  const int *L = L0.geo.L; long V = L0.geo.V;
-  std::vector<double> &h = A->stage;
-  h.resize((size_t)V * 24);
+  long V = L0.geo.V;
   if (A->vector_index_fct) {
-    long j = 0;
-    for (int t = 0; t < L[0]; t++) for (int z = 0; z < L[1]; z++) for (int y = 0; y < L[2]; y++) for (int x = 0; x < L[3]; x++) {
-      long i = A->vector_index_fct(t, z, y, x);
-      memcpy(&h[j], in + i, 24 * sizeof(double)); j += 24;
-    }
+    std::vector<double> &h = A->stage;
+    h.resize((size_t)V * 24);
+    const std::vector<long> &off = vector_offsets();
+#pragma omp parallel for schedule(static)
+    for (long j = 0; j < V; j++) memcpy(&h[24 * j], in + off[j], 24 * sizeof(double));
     h2d(s.lexbuf, h.data(), sizeof(cd) * 12 * V);
   } else h2d(s.lexbuf, in, sizeof(cd) * 12 * V);
   spinor_from_lex<double>(L0.geo, dev_native, s.lexbuf, 12);
 }
 static void scatter_solution(double *out, const cd *dev_native) {
   Solver &s = A->s; Level &L0 = s.lev[0];
-  const int *L = L0.geo.L; long V = L0.geo.V;
+  long V = L0.geo.V;
   spinor_to_lex<double>(L0.geo, s.lexbuf, dev_native, 12);
   if (A->vector_index_fct) {
     std::vector<double> &h = A->stage;
     h.resize((size_t)V * 24);
     d2h(h.data(), s.lexbuf, sizeof(cd) * 12 * V);
-    long j = 0;
-    for (int t = 0; t < L[0]; t++) for (int z = 0; z < L[1]; z++) for (int y = 0; y < L[2]; y++) for (int x = 0; x < L[3]; x++) {
-      long i = A->vector_index_fct(t, z, y, x);
-      memcpy(out + i, &h[j], 24 * sizeof(double)); j += 24;
-    }
+    const std::vector<long> &off = vector_offsets();
+#pragma omp parallel for schedule(static)
+    for (long j = 0; j < V; j++) memcpy(out + off[j], &h[24 * j], 24 * sizeof(double));
   } else d2h(out, s.lexbuf, sizeof(cd) * 12 * V);
 }
 

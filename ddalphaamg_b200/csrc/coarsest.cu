@@ -88,6 +88,7 @@ void coarsest_alloc(Solver &s) {
     else C.hostk.op = [sp](cf *out, const cf *in) { mg_apply_op(*sp, sp->nlev - 1, out, in); };
   } else {
     C.dg.alloc(nsolve, p.coarse_iter, p.coarse_restart, p.coarse_tol, na);
+    C.dg.reduce_over_ranks = C.geo->partitioned();        // gathered / single-rank lattice: every rank has the whole vectors
     if (p.odd_even) C.dg.op = [sp](cf *out, const cf *in, const int *skip) { mg_coarsest_schur(*sp, out, in, skip); };
     else C.dg.op = [sp](cf *out, const cf *in, const int *) { mg_apply_op(*sp, sp->nlev - 1, out, in); };
 #ifndef DDA_HOST_EMU

@@ -3,7 +3,7 @@
 // Product build: nvcc -gencode arch=compute_100a,code=sm_100a (all kernels run on the GPU, no CPU fallback).
 // Test-only build: g++ -x c++ -DDDA_HOST_EMU compiles the *same* host logic with kernels executed as host
 // loops, so the control flow (cycles, Krylov, setup) can be unit-tested in the GPU-less container.  The
-// emulation library is never loaded by the product package (see tests/emu_build.py).
+// emulation library is never loaded by the product package (built by ddalphaamg_b200/build.py --emu into tests/_emu).
 #pragma once
 #include <cstdio>
 #include <cstdlib>

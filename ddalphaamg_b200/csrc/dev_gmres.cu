@@ -48,7 +48,7 @@ int DevGmres::solve(cf *x, const cf *b) {
     if (ol == 0) vcopy(ww, b, nn);
     else { op(ww, x, nullptr); launch_n(nn, DLAMBDA(long i) { ww[i] = b[i] - ww[i]; }); }
     launch_reduce<1>(1, nn, DLAMBDA(long seg, long i, double *acc) { (void)seg; cf a = ww[i]; acc[0] += (double)a.re * a.re + (double)a.im * a.im; }, S + o.N);
-    comm_allreduce_sum(S + o.N, 1);
+    if (reduce_over_ranks) comm_allreduce_sum(S + o.N, 1);
     launch_n(1, DLAMBDA(long) {
       const double g0 = sqrt(S[o.N]);
       S[o.G] = g0; S[o.G + 1] = 0.0;
@@ -75,7 +75,7 @@ int DevGmres::solve(cf *x, const cf *b) {
         acc[0] += (double)a.re * c.re + (double)a.im * c.im;
         acc[1] += (double)a.re * c.im - (double)a.im * c.re;
       }, S + o.HB);
-      comm_allreduce_sum(S + o.HB, 2 * (j + 1));
+      if (reduce_over_ranks) comm_allreduce_sum(S + o.HB, 2 * (j + 1));
       // w -= sum_k hbuf[k] V_k and ||w||^2 in one pass
       launch_reduce<1>(1, nn, DLAMBDA(long seg, long i, double *acc) {
         (void)seg;
@@ -84,7 +84,7 @@ int DevGmres::solve(cf *x, const cf *b) {
         ww[i] = v;
         acc[0] += (double)v.re * v.re + (double)v.im * v.im;
       }, S + o.N);
-      comm_allreduce_sum(S + o.N, 1);
+      if (reduce_over_ranks) comm_allreduce_sum(S + o.N, 1);
       // Hessenberg column, Givens rotations, convergence test (qr_update, linsolve_generic.c:898-940)
       launch_n(1, DLAMBDA(long) { gmres_givens(S, ct, o, j, tl); });
       }

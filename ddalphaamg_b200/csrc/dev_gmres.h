@@ -63,6 +63,7 @@ struct DevGmres {
   int m = 0, max_restart = 0;
   double tol = 0;
   bool allocated = false;
+  bool reduce_over_ranks = true;   // false: every rank holds the WHOLE vectors (gathered coarsest level): local reductions are global
   cf *V = nullptr;        // m+1 basis vectors, stride `stride` (>= n: room for ghost slabs)
   cf *w = nullptr;
   double *st = nullptr;   // device scalars, see offsets in dev_gmres.cu

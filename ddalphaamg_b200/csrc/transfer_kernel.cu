@@ -58,7 +58,42 @@ k_restrict_fine(Transfer t, cf *__restrict__ out, long site_stride, long offset,
     out[(long)t.agg2coarse[a] * site_stride + offset + i] = cf(acc_s[2 * i], acc_s[2 * i + 1]);
 }
 
+// coarse levels (site-major vectors, nc = 2 Nv' dofs per site): one CTA per aggregate, phi of the aggregate in shared memory,
+// every warp takes output components (chirality, k) = w, w + 8, ... and streams P_k over the aggregate with coalesced loads
+// (the generic path launches one CTA row per (aggregate, component): 0.15 of the HBM roofline at level 1).
+__global__ void __launch_bounds__(256)
+k_restrict_coarse(Transfer t, cf *__restrict__ out, long site_stride, long offset, const cf *__restrict__ phi) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf *ps = reinterpret_cast<cf *>(smem_raw);
+  const int a = blockIdx.x, as = t.as, nv = t.nv, nc = t.nc, h = nc / 2;
+  const int len = as * nc, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long base = (long)a * len;
+  for (int q = threadIdx.x; q < len; q += 256) ps[q] = phi[base + q];
+  __syncthreads();
+  const int per = as * h;                                     // elements of one chirality in the aggregate
+  for (int j = w; j < 2 * nv; j += 8) {
+    const int ch = j / nv, k = j - ch * nv;
+    const cf *__restrict__ P = t.P[k] + base;
+    float ar = 0.f, ai = 0.f;
+    for (int e = lane; e < per; e += 32) {
+      const int sl = e / h, q = sl * nc + ch * h + (e - sl * h);
+      const float2 p = __ldg(reinterpret_cast<const float2 *>(P + q));
+      const cf v = ps[q];
+      ar = __fmaf_rn(p.y, v.im, __fmaf_rn(p.x, v.re, ar));    // conj(P) * phi
+      ai = __fmaf_rn(-p.y, v.re, __fmaf_rn(p.x, v.im, ai));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ar += __shfl_xor_sync(0xffffffffu, ar, o); ai += __shfl_xor_sync(0xffffffffu, ai, o); }
+    if (lane == 0) out[(long)t.agg2coarse[a] * site_stride + offset + j] = cf(ar, ai);
+  }
+}
+
 bool tr_restrict_fast(const Transfer &t, cf *out, long site_stride, long offset, const cf *phi) {
+  if (t.lay.sh == 0 && (t.nc & 1) == 0 && (size_t)t.as * t.nc * sizeof(cf) <= 48 * 1024) {
+    k_restrict_coarse<<<t.nagg, 256, (size_t)t.as * t.nc * sizeof(cf), g_stream>>>(t, out, site_stride, offset, phi);
+    g_launch_count++;
+    return true;
+  }
   if (!(t.lay.sh == 5 && t.nc == 12 && t.as % 32 == 0)) return false;
   int block = t.as >= 256 ? 256 : t.as;
   k_restrict_fine<4><<<t.nagg, block, 0, g_stream>>>(t, out, site_stride, offset, phi);
