@@ -16,6 +16,22 @@ from ddalphaamg_b200 import DDalphaAMG, random_gauge_field, BENCH, INFO  # noqa:
 def main():
     case = sys.argv[1] if len(sys.argv) > 1 else "sap"
     lat = [64, 32, 32, 32]
+    if case == "sap48":
+        lat = [96, 48, 48, 48]          # the benchmark's lattice: 20736 block visits per launch
+        case = "sap"
+    if case == "mrhs":
+        S = DDalphaAMG(lat, [4, 4, 4, 4], levels=3, test_vectors=(20, 28), setup_iter=(1, 1), restart=10, m0=-0.35, csw=1.0,
+                       mixed_precision=2, coarse_block=[2, 2, 2, 2])
+        S.set_conf(random_gauge_field(lat, seed=20261018, eps=0.3))
+        S.setup(0)
+        rng = np.random.default_rng(3)
+        for d in (1, 2):
+            V, nc = S.level_shape(d)
+            vs = (rng.standard_normal((12, V * nc)) + 1j * rng.standard_normal((12, V * nc))).astype(np.complex64)
+            o, ms = S.level_apply_mrhs(d, vs, reps=3)
+            print("mrhs depth", d, "ms per 12-RHS apply", ms, "single", S.bench_op(BENCH.LEVEL_APPLY, d, 3))
+        S.free()
+        return
     if case == "sap":
         S = DDalphaAMG(lat, [4, 4, 4, 4], levels=2, test_vectors=(4,), setup_iter=(0,), restart=10, m0=-0.35, csw=1.0, mixed_precision=2)
         S.set_conf(random_gauge_field(lat, seed=20261018, eps=0.3))
@@ -27,6 +43,8 @@ def main():
         S.set_conf(random_gauge_field(lat, seed=20261018, eps=0.3))
         S.setup(0)
         nlev = S.info(INFO.NUM_LEVELS)
+        import torch
+        torch.cuda.profiler.start()      # ncu --profile-from-start off: only the operator applications below
         print("dw double", S.bench_op(BENCH.DW_DOUBLE, 0, 2), "float", S.bench_op(BENCH.DW_FLOAT, 0, 2))
         for d in range(1, nlev):
             print("apply", d, S.bench_op(BENCH.LEVEL_APPLY, d, 2))
@@ -34,6 +52,7 @@ def main():
             print("restrict", d, S.bench_op(BENCH.RESTRICT, d, 2), "interpolate", S.bench_op(BENCH.INTERPOLATE, d, 2))
         print("sap d1", S.bench_op(BENCH.SMOOTHER, 1, 2))
         print("schur", S.bench_op(BENCH.COARSEST_SCHUR, nlev - 1, 4))
+        torch.cuda.profiler.stop()
     S.free()
 
 
