@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdd_alpha_amg.so")
 EMU_DIR = os.path.join(ROOT, "tests", "_emu")
 EMU_LIB = os.path.join(EMU_DIR, "libdda_emu.so")
-GPU_ONLY = ("dw_kernel.cu", "coarse_kernel.cu", "sap_kernel.cu", "transfer_kernel.cu", "schur_kernel.cu", "mrhs_kernel.cu", "comm.cu")
+GPU_ONLY = ("dw_kernel.cu", "coarse_kernel.cu", "sap_kernel.cu", "transfer_kernel.cu", "schur_kernel.cu", "mrhs_kernel.cu", "galerkin_kernel.cu", "comm.cu")
 
 
 def _newer(target, sources):

@@ -19,6 +19,20 @@ static void vrandom(cf *v, long n, unsigned long long seed) {
   launch_n(n, DLAMBDA(long i) { v[i] = cf(u01(seed + 2ULL * i), u01(seed + 2ULL * i + 1ULL)); });
 }
 
+#ifndef DDA_HOST_EMU
+bool galerkin_fine_fast(const FineOp<float> &op, const Transfer &t, cf *S, cf *F);
+static int g_galerkin_fast = []() { const char *e = getenv("DDA_GALERKIN_FAST"); return e ? atoi(e) : 1; }();
+#endif
+
+// setup phase timers (DDA_SETUP_PROFILE=1: device-synchronising, printed at the end of mg_setup)
+static int g_setup_profile = []() { const char *e = getenv("DDA_SETUP_PROFILE"); return e ? atoi(e) : 0; }();
+static double g_t_setup[6] = {0, 0, 0, 0, 0, 0};   // 0 test-vector smoothing, 1 interpolation (Gram-Schmidt), 2 Galerkin, 3 bootstrap cycles, 4 global GS, 5 other
+struct SetupTimer {
+  int k; double t0;
+  explicit SetupTimer(int k_) : k(k_), t0(0) { if (g_setup_profile) { dev_sync(); t0 = now_s(); } }
+  ~SetupTimer() { if (g_setup_profile) { dev_sync(); g_t_setup[k] += now_s() - t0; } }
+};
+
 static void build_transfer(Level &L, Level &N) {
   Transfer &t = L.tr;
   t.lay = L.geo.lay(); t.V = L.geo.V; t.nc = L.geo.nc; t.nv = L.nv; t.nagg = L.geo.nagg; t.as = L.geo.as;
@@ -111,12 +125,21 @@ void mg_free(Solver &s) {
 // One operator application + one restriction per coarse column and coupling (the reference assembles the same
 // products column by column, coarse_operator_generic.c:53-205).
 void mg_rebuild_coarse(Solver &s, int depth) {
+  SetupTimer st_(2);
   Level &L = s.lev[depth], &N = s.lev[depth + 1];
   CoarseOp &c = N.cop;
   const int n = c.n, nv = L.nv; const long nn = (long)n * n;
   cf *w0 = L.w[6], *w1 = L.w[7];
   SiteSel all = sel_all(L.geo.V);
-  for (int j = 0; j < n; j++) {
+  bool done = false;
+#ifndef DDA_HOST_EMU
+  if (depth == 0 && s.use_fast && g_galerkin_fast) {
+    // fused construction (galerkin_kernel.cu): all columns in one launch, no intermediate vectors
+    for (int k = 0; k < nv; k++) lv_halo(L, L.P[k]);
+    done = galerkin_fine_fast(L.opf, L.tr, c.S, c.F);
+  }
+#endif
+  for (int j = 0; j < n && !done; j++) {
     int ch = j / nv, k = j - ch * nv;
     tr_chirality_part(L.tr, w0, L.P[k], ch);
     lv_halo(L, w0);
@@ -132,6 +155,7 @@ void mg_rebuild_coarse(Solver &s, int depth) {
 }
 
 static void define_interpolation(Solver &s, int depth) {
+  SetupTimer st_(1);
   Level &L = s.lev[depth];
   const long n = L.geo.vlen();
   for (int k = 0; k < L.nv; k++) vcopy(L.P[k], L.tv[k], n);
@@ -155,6 +179,7 @@ static void normalise(cf *v, long n) {
 // initial test vectors of a level: random vectors smoothed by 1+2+3 SAP iterations (setup_generic.c:215-231)
 // (on every level: the restricted finer test vectors are overwritten by random ones in the reference, too)
 static void initial_test_vectors(Solver &s, int depth) {
+  SetupTimer st_(0);
   Level &L = s.lev[depth];
   const long n = L.geo.vlen();
   cf *buf = L.w[8];
@@ -170,6 +195,7 @@ static void initial_test_vectors(Solver &s, int depth) {
 
 // global Gram-Schmidt on the test vectors (gram_schmidt_PRECISION, linalg_generic.c:356-397)
 static void gram_schmidt_global(Level &L) {
+  SetupTimer st_(4);
   const long n = L.geo.vlen();
   std::vector<cd> co(L.nv);
   for (int k = 0; k < L.nv; k++) {
@@ -191,7 +217,7 @@ static void bootstrap(Solver &s, int depth, int setup_iter) {
     gram_schmidt_global(L);
     for (int i = 0; i < L.nv; i++) {
       // one cycle with the test vector as right-hand side; every level keeps its iterate as new test vector
-      mg_vcycle(s, depth, L.vx, L.tv[i], true);
+      { SetupTimer st_(3); mg_vcycle(s, depth, L.vx, L.tv[i], true); }
       for (int d = s.nlev - 2; d > depth; d--) {
         // test_vector_PRECISION_update (setup_generic.c:428-438): deeper levels take the solution of their last solve
         Level &D = s.lev[d];
@@ -263,6 +289,11 @@ void mg_setup(Solver &s, int setup_iters) {
   }
   if (m_solve != s.m0_op) solver_shift_mass(s, m_solve);
   dev_sync();
+  if (g_setup_profile) {
+    fprintf(stderr, "dd_alpha_amg_b200 setup phases [s]: test-vector smoothing %.3f, aggregate Gram-Schmidt %.3f, Galerkin %.3f, bootstrap cycles %.3f (nested levels included), global Gram-Schmidt %.3f\n",
+            g_t_setup[0], g_t_setup[1], g_t_setup[2], g_t_setup[3], g_t_setup[4]);
+    for (double &t : g_t_setup) t = 0;
+  }
 }
 
 void mg_resetup_from_test_vectors(Solver &s) {

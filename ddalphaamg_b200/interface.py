@@ -109,6 +109,14 @@ def load_library(path=None):
     if not os.path.exists(path):
         raise RuntimeError("%s not found: build the CUDA library with `python -m ddalphaamg_b200.build` "
                            "(there is no CPU fallback)" % path)
+    if os.path.basename(os.path.dirname(os.path.abspath(path))) != "_emu":
+        # The CUDA library links the system NCCL; torch bundles a newer one.  If torch is going to be used in this process
+        # (bench.py, the multi-rank tests) it has to be imported BEFORE the library, or libtorch_cuda fails to resolve its
+        # NCCL symbols.  A C caller without Python is not affected.
+        try:
+            import torch  # noqa: F401
+        except ImportError:
+            pass
     L = C.CDLL(path, mode=C.RTLD_LOCAL)
     L.dda_is_emulation.restype = C.c_int
     if L.dda_is_emulation() and os.path.basename(os.path.dirname(os.path.abspath(path))) != "_emu":

@@ -7,6 +7,7 @@ import os
 import sys
 
 import numpy as np
+import torch  # noqa: F401  (before the library: torch bundles its own NCCL, which must be the first one the process loads)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -43,7 +44,6 @@ def main():
         S.set_conf(random_gauge_field(lat, seed=20261018, eps=0.3))
         S.setup(0)
         nlev = S.info(INFO.NUM_LEVELS)
-        import torch
         torch.cuda.profiler.start()      # ncu --profile-from-start off: only the operator applications below
         print("dw double", S.bench_op(BENCH.DW_DOUBLE, 0, 2), "float", S.bench_op(BENCH.DW_FLOAT, 0, 2))
         for d in range(1, nlev):
