@@ -21,7 +21,7 @@
 // fp32 accuracy on TF32 hardware: every operand is split x = hi + lo (hi = 11 significant bits) and each product is three
 // MMAs hi*hi + lo*hi + hi*lo accumulated in the same fp32 TMEM accumulator (error ~2^-21 relative).
 //
-// Per CTA (128 threads, persistent over sites): TMA bulk copies stream the raw blocks into a ring (cp.async.bulk + mbarrier,
+// Per CTA (256 threads, persistent over sites): TMA bulk copies stream the raw blocks into a ring (cp.async.bulk + mbarrier,
 // as in coarse_kernel.cu); all threads re-tile the block (with the hi/lo split) and the right-hand sides into operand
 // buffers; ONE thread issues the tcgen05.mma sequence and commits it to an mbarrier; accumulators live in TMEM (forward:
 // 128 lanes x 32 columns, daggered: 4 x 32 columns) and are read back with tcgen05.ld for the epilogue.  The daggered
@@ -108,8 +108,10 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
 //   Bf: [Re V | Im V], N = 32 right-hand-side slots (4 row groups), K = c;   Bd: [w | -i w], K = rho
 const int AD_FLOATS = 8 * 32 * 32;
 
+const int NT = 256;                      // threads per CTA (8 warps: re-tiling and operand fills are what the CTA spends its time on)
+
 template <int STAGES>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(NT)
 k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *__restrict__ Z, long vstride, long zstride, int nsites) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int n = op.n, nn = n * n, nh = n / 2, n2 = 2 * n;
@@ -132,7 +134,7 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
   const int my_sites = (nsites - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total = 5 * my_sites;
 
-  for (int q = tid; q < 2 * AF_FLOATS + 2 * AD_FLOATS + 8 * (kcf + kcd) * 32; q += 128) Afh[q] = 0.f;   // padding stays zero
+  for (int q = tid; q < 2 * AF_FLOATS + 2 * AD_FLOATS + 8 * (kcf + kcd) * 32; q += NT) Afh[q] = 0.f;   // padding stays zero
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
     mbar_init(mma_done, 1);
@@ -164,7 +166,7 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
   uint32_t mma_phase = 0;
 
   // the right-hand sides a block multiplies (12 x n complex) are fetched one block ahead into registers
-  const int NPRE = 6;                                               // 12 * 64 / 128
+  const int NPRE = 3;                                               // 12 * 64 / NT
   cf pre[NPRE];
   auto prefetch = [&](int j) {                                      // vectors of block j: site x (S) or x + mu (F_mu)
     const int k = j / 5, m = j - 5 * k;
@@ -172,7 +174,7 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
     const long src = (m == 0) ? x : (long)op.nb[(long)(m - 1) * op.V + x];
 #pragma unroll
     for (int i = 0; i < NPRE; i++) {
-      const int q = tid + 128 * i;
+      const int q = tid + NT * i;
       if (q < NR * n) { const int jr = q / n, c = q - jr * n; pre[i] = in[(long)jr * vstride + src * n + c]; }
     }
   };
@@ -186,7 +188,7 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
       // the daggered operand B' = [w | -i w], w = G5 V(x), is filled as well (rows j and 12 + j, K = rho = 2 r + re|im)
 #pragma unroll
       for (int i = 0; i < NPRE; i++) {
-        const int q = tid + 128 * i;
+        const int q = tid + NT * i;
         if (q < NR * n) {
           const int jr = q / n, c = q - jr * n;
           const cf v = pre[i];
@@ -215,14 +217,17 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
       }
       if (j + 1 < total) prefetch(j + 1);
       mbar_wait_bounded(&full[st], (uint32_t)((j / STAGES) & 1));
-      // re-tile the raw block (column-major complex = real W[rho][c], rho fastest): 16-byte chunk (column c, rho = 4g..4g+3)
-      //   daggered view: core matrix (c / 8, g), row c % 8          (one 16-byte store)
-      //   forward view:  element (rho, c) -> core (rho / 8, c / 4), row rho % 8, position c % 4   (four scalar stores)
-      // lanes: c % 4 = lane % 4, g % 2 = (lane / 4) % 2 -> the scalar stores of one instruction hit 8 distinct banks
-      {
-        const float4 *R4 = reinterpret_cast<const float4 *>(raw + (size_t)st * nn);
-        const int ncq = n >> 2, ngq = kcd >> 1, combos = ncq * ngq;
-        for (int u = warp * 4 + (lane >> 3); u < combos; u += 16) {
+      // re-tile the raw block (column-major complex = real W[rho][c], rho fastest) in two passes, each followed by its MMAs, so
+      // that the tensor core works on the daggered product while the threads build the forward operand:
+      //   pass 1, daggered view: 16-byte chunk (column c, rho = 4g..4g+3) -> core matrix (c / 8, g), row c % 8   (one 16-byte store)
+      //   pass 2, forward view:  element (rho, c) -> core (rho / 8, c / 4), row rho % 8, position c % 4          (four scalar stores)
+      // lanes: c % 4 = lane % 4, g % 2 = (lane / 4) % 2, and in store step t lane group r = lane / 8 writes rho = 4 g + (t + r) % 4:
+      // the 32 lanes of a scalar store hit 32 distinct banks (the first version of this kernel lost 71 % of its shared-memory
+      // wavefronts to conflicts here, profiles/r2_ncu_full_k_coarse_mrhs_a.txt)
+      const float4 *R4 = reinterpret_cast<const float4 *>(raw + (size_t)st * nn);
+      const int ncq = n >> 2, ngq = kcd >> 1, combos = ncq * ngq;
+      if (m > 0) {
+        for (int u = warp * 4 + (lane >> 3); u < combos; u += 4 * (NT / 32)) {
           const int cq = u / ngq, gq = u - cq * ngq;
           const int c = 4 * cq + (lane & 3), g = 2 * gq + ((lane >> 2) & 1);
           const float4 v = R4[c * kcd + g];
@@ -231,21 +236,47 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
           const int od = ((c >> 3) * 32 + g) * 32 + (c & 7) * 4;
           *reinterpret_cast<float4 *>(Adh + od) = h;
           *reinterpret_cast<float4 *>(Adl + od) = l;
-          const float hv[4] = {h.x, h.y, h.z, h.w}, lv[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-          for (int t = 0; t < 4; t++) {
-            const int rho = 4 * g + t;
-            const int of = ((rho >> 3) * kcf + (c >> 2)) * 32 + (rho & 7) * 4 + (c & 3);
-            Afh[of] = hv[t]; Afl[of] = lv[t];
-          }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // operand buffers written by the generic proxy
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
+      if (tid == 0 && m > 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // daggered: D_mu[c][slot] = sum_rho W[rho][c] B'[slot][rho]; K = 2n, 8 per MMA = two cores (256 B) of A and of B
+        const uint32_t td = tmem + 32u * (uint32_t)m;
+        for (int ks = 0; ks < n2 / 8; ks++) {
+          const uint32_t o = (uint32_t)ks * 256;
+          const uint64_t ah = smem_desc(aAdh + o, 128, 4096), al = smem_desc(aAdl + o, 128, 4096);
+          const uint64_t bh = smem_desc(aBdh + o, 128, (uint32_t)kcd * 128), bl = smem_desc(aBdl + o, 128, (uint32_t)kcd * 128);
+          mma_tf32(td, ah, bh, idesc, ks > 0 ? 1u : 0u);
+          mma_tf32(td, al, bh, idesc, 1u);
+          mma_tf32(td, ah, bl, idesc, 1u);
+        }
+      }
+      {
+        const int r = lane >> 3;
+        for (int u = warp * 4 + r; u < combos; u += 4 * (NT / 32)) {
+          const int cq = u / ngq, gq = u - cq * ngq;
+          const int c = 4 * cq + (lane & 3), g = 2 * gq + ((lane >> 2) & 1);
+          const float4 v = R4[c * kcd + g];
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            const int tt = (t + r) & 3;
+            const float x = tt == 0 ? v.x : (tt == 1 ? v.y : (tt == 2 ? v.z : v.w));
+            float hi, lo; split_tf32(x, hi, lo);
+            const int rho = 4 * g + tt;
+            const int of = ((rho >> 3) * kcf + (c >> 2)) * 32 + (rho & 7) * 4 + (c & 3);
+            Afh[of] = hi; Afl[of] = lo;
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // forward: D_fwd[rho][slot] += sum_c W[rho][c] B[slot][c]; K = n, 8 per MMA = two cores (256 B) of A and of B
+        // forward: D_fwd[rho][slot] += sum_c W[rho][c] B[slot][c]; K = n
         for (int ks = 0; ks < n / 8; ks++) {
           const uint32_t o = (uint32_t)ks * 256;
           const uint64_t ah = smem_desc(aAfh + o, 128, (uint32_t)kcf * 128), al = smem_desc(aAfl + o, 128, (uint32_t)kcf * 128);
@@ -254,18 +285,6 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
           mma_tf32(tmem, al, bh, idesc, 1u);
           mma_tf32(tmem, ah, bl, idesc, 1u);
         }
-        if (m > 0) {
-          // daggered: D_mu[c][slot] = sum_rho W[rho][c] B'[slot][rho]; K = 2n
-          const uint32_t td = tmem + 32u * (uint32_t)m;
-          for (int ks = 0; ks < n2 / 8; ks++) {
-            const uint32_t o = (uint32_t)ks * 256;
-            const uint64_t ah = smem_desc(aAdh + o, 128, 4096), al = smem_desc(aAdl + o, 128, 4096);
-            const uint64_t bh = smem_desc(aBdh + o, 128, (uint32_t)kcd * 128), bl = smem_desc(aBdl + o, 128, (uint32_t)kcd * 128);
-            mma_tf32(td, ah, bh, idesc, ks > 0 ? 1u : 0u);
-            mma_tf32(td, al, bh, idesc, 1u);
-            mma_tf32(td, ah, bl, idesc, 1u);
-          }
-        }
         mma_commit(mma_done);                                        // arrives when every MMA issued so far has completed
       }
       mbar_wait_bounded(mma_done, mma_phase & 1);                    // operand buffers and the raw stage are free again
@@ -273,23 +292,27 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (tid == 0 && j + STAGES < total) issue(j + STAGES);
     }
-    // epilogue: accumulators -> registers -> global.  Thread = TMEM lane = row of the accumulator.
+    // epilogue: accumulators -> registers -> global.  A warp reaches the TMEM lanes 32 (warp % 4) .. +31 = rows of the
+    // accumulators; warps 0-3 take the forward accumulator and the daggered ones of mu = 0, 1, warps 4-7 those of mu = 2, 3.
     {
-      const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+      const int row = (warp & 3) * 32 + lane;
+      const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
       float v[32];
-      tmem_ld32(tmem + lane_base, v);
-      // forward rows rho = 2 r + (re|im): Re Y = P[2r][j] - P[2r+1][12+j], Im Y = P[2r+1][j] + P[2r][12+j]
-      const int rho = tid, r = rho >> 1, im = rho & 1;
+      if (warp < 4) {
+        tmem_ld32(tmem + lane_base, v);
+        // forward rows rho = 2 r + (re|im): Re Y = P[2r][j] - P[2r+1][12+j], Im Y = P[2r+1][j] + P[2r][12+j]
+        const int rho = row, r = rho >> 1, im = rho & 1;
 #pragma unroll
-      for (int j = 0; j < NR; j++) {
-        const float other = __shfl_xor_sync(0xffffffffu, v[NR + j], 1);     // partner row's [12 + j] entry
-        const float val = im ? v[j] + other : v[j] - other;
-        if (rho < n2) reinterpret_cast<float *>(out + (long)j * vstride + x * n + r)[im] = val;
+        for (int j = 0; j < NR; j++) {
+          const float other = __shfl_xor_sync(0xffffffffu, v[NR + j], 1);     // partner row's [12 + j] entry
+          const float val = im ? v[j] + other : v[j] - other;
+          if (rho < n2) reinterpret_cast<float *>(out + (long)j * vstride + x * n + r)[im] = val;
+        }
       }
 #pragma unroll 1
-      for (int mu = 0; mu < 4; mu++) {
+      for (int mu = (warp < 4 ? 0 : 2); mu < (warp < 4 ? 2 : 4); mu++) {
         tmem_ld32(tmem + lane_base + 32u * (uint32_t)(1 + mu), v);
-        const int c = tid;
+        const int c = row;
         if (c < n) {
           const float sg = (c < nh) ? 1.f : -1.f;
 #pragma unroll
@@ -326,7 +349,7 @@ bool coarse_apply_mrhs(const CoarseOp &op, cf *out, const cf *in, cf *Z, long vs
   const int per_sm = (int)std::min<size_t>(2, (227 * 1024) / (smem + 1024));    // TMEM: 2 x 256 columns per SM
   if (per_sm < 1) return false;
   const long grid = std::min<long>(op.V, (long)sms * per_sm);
-  mrhs::k_coarse_mrhs<2><<<(unsigned)grid, 128, smem, g_stream>>>(op, out, in, Z, vstride, zstride, (int)op.V);
+  mrhs::k_coarse_mrhs<2><<<(unsigned)grid, mrhs::NT, smem, g_stream>>>(op, out, in, Z, vstride, zstride, (int)op.V);
   g_launch_count++;
   for (int j = 0; j < mrhs::NR; j++) coarse_combine(op, out + (long)j * vstride, in + (long)j * vstride, Z + (long)j * zstride);
 #ifdef DDA_DEBUG_SYNC
