@@ -318,6 +318,7 @@ void dd_alpha_amg_free(void) {
   s.outer.release();
   s.outer_mp.release();
   solver_free_fine(s);
+  halo_finalize();
   delete A; A = nullptr; g_solver = nullptr;
 }
 

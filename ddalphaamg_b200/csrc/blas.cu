@@ -92,7 +92,7 @@ template <class T> static void vmulti_dot_chunk(cd *out, cx<T> *const *V, int m,
   if (n >= (1L << 16)) {
     dev_zero(buf, sizeof(double) * 2 * m);
     const int KB = 8;
-    long blocks = std::min<long>((n + 255) / 256, 148L * 8);
+    long blocks = std::min<long>((n + 255) / 256, (long)dev_sm_count() * 8);
     for (int k0 = 0; k0 < m; k0 += KB) {
       k_multi_dot<T, KB><<<(unsigned)blocks, 256, 0, g_stream>>>(pa, k0, std::min(KB, m - k0), w, n, buf);
       g_launch_count++;

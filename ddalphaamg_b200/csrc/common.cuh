@@ -118,6 +118,7 @@ void d2h(void *dst, const void *src, size_t bytes);
 void d2d(void *dst, const void *src, size_t bytes);
 void dev_sync();
 size_t dev_bytes_in_use();
+int dev_sm_count();            // multiprocessors of the current device (queried once; 1 in the emulation build)
 template <class T> T *dev_alloc(size_t n) { return (T *)dev_alloc_bytes(n * sizeof(T)); }
 template <class T> T *dev_upload(const std::vector<T> &v) { T *p = dev_alloc<T>(v.size() ? v.size() : 1); if (v.size()) h2d(p, v.data(), v.size() * sizeof(T)); return p; }
 
@@ -170,7 +171,7 @@ template <int NV, class F> void launch_reduce(long nseg, long seglen, F f, doubl
   dev_zero(out, sizeof(double) * NV * nseg);
   if (seglen <= 0) return;
   int block = seglen >= 256 ? 256 : (seglen >= 128 ? 128 : 64);
-  long want = (148L * 8 + nseg - 1) / nseg;               // aim for >= 8 CTAs per SM overall
+  long want = ((long)dev_sm_count() * 8 + nseg - 1) / nseg;   // aim for >= 8 CTAs per SM overall
   long maxc = (seglen + block * 4L - 1) / (block * 4L);   // at least 4 elements per thread
   long chunks = std::max(1L, std::min(want, std::min(maxc, 65535L)));
   dim3 grid((unsigned)nseg, (unsigned)chunks);

@@ -48,19 +48,29 @@ template <class E> void halo_begin(const Geometry &g, E *v, int nc, int sh) {
   comm_buffer(0, sizeof(E) * (size_t)smax * nc); comm_buffer(1, sizeof(E) * (size_t)smax * nc);   // grow (may sync) before forking
   CUDA_CHECK(cudaEventRecord(g_ev_ready, g_stream));
   CUDA_CHECK(cudaStreamWaitEvent(g_halo_stream, g_ev_ready, 0));
-  cudaStream_t compute = g_stream;
-  g_stream = g_halo_stream;                 // pack kernel + NCCL calls of halo_exchange go to the second stream
-  halo_exchange<E>(g, v, nc, sh);
-  g_stream = compute;
+  {
+    // pack kernel + NCCL calls of halo_exchange go to the second stream: the library's current stream is switched for the
+    // scope of this block (single host thread; halo_end always precedes the next collective on the compute stream)
+    struct StreamScope { cudaStream_t saved; StreamScope(cudaStream_t s) : saved(g_stream) { g_stream = s; } ~StreamScope() { g_stream = saved; } } scope(g_halo_stream);
+    halo_exchange<E>(g, v, nc, sh);
+  }
   CUDA_CHECK(cudaEventRecord(g_ev_done, g_halo_stream));
 }
 void halo_end(const Geometry &g) {
   if (!g.partitioned()) return;
   CUDA_CHECK(cudaStreamWaitEvent(g_stream, g_ev_done, 0));
 }
+void halo_finalize() {
+  if (g_halo_stream) {
+    cudaStreamSynchronize(g_halo_stream);
+    cudaEventDestroy(g_ev_ready); cudaEventDestroy(g_ev_done); cudaStreamDestroy(g_halo_stream);
+    g_halo_stream = nullptr; g_ev_ready = g_ev_done = nullptr;
+  }
+}
 #else
 template <class E> void halo_begin(const Geometry &g, E *v, int nc, int sh) { halo_exchange<E>(g, v, nc, sh); }
 void halo_end(const Geometry &) {}
+void halo_finalize() {}
 #endif
 template void halo_begin<cf>(const Geometry &, cf *, int, int);
 template void halo_begin<cd>(const Geometry &, cd *, int, int);

@@ -15,6 +15,7 @@ template <class E> void halo_exchange(const Geometry &g, E *v, int nc, int sh);
 // wait for the exchange.  Without a GPU build (host emulation) halo_begin does the whole exchange and halo_end nothing.
 template <class E> void halo_begin(const Geometry &g, E *v, int nc, int sh);
 void halo_end(const Geometry &g);
+void halo_finalize();    // destroys the second stream and its events (recreated on demand); called by dd_alpha_amg_free / comm_finalize
 extern long g_halo_bytes;   // bytes sent by this rank (statistics)
 
 }  // namespace dda

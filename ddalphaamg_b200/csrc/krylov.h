@@ -209,7 +209,9 @@ struct FgmresMP {
         vzero(w, n);
         vmulti_axpy(w, B.data(), y.data(), j + 1, +1, n);
         vcast(r, w, n);
-        if (ol == 0) vcopy(x, r, n); else vadd(x, x, r, n);
+        // the reference assigns in the first restart cycle whatever the initial guess was (linsolve.c fgmres_MP); a caller's
+        // non-zero guess must be kept, so only a zero guess is overwritten
+        if (ol == 0 && zero_guess) vcopy(x, r, n); else vadd(x, x, r, n);
       }
       last_relres = gamma_jp1 / norm_r0;
     }

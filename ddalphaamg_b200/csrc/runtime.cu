@@ -53,5 +53,14 @@ void d2d(void *dst, const void *src, size_t bytes) { memmove(dst, src, bytes); }
 void dev_sync() {}
 #endif
 size_t dev_bytes_in_use() { return g_bytes; }
+int dev_sm_count() {
+#ifndef DDA_HOST_EMU
+  static int sms = 0;
+  if (!sms) { int dev = 0; CUDA_CHECK(cudaGetDevice(&dev)); CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+  return sms;
+#else
+  return 1;
+#endif
+}
 
 }  // namespace dda
