@@ -34,3 +34,28 @@ def test_parity_slabs_match_reference_operator(emu_lib, oracle_ref, tmp_path):
         assert par2.get("ok") is False and par2["residual_ref_operator"] > 1.5e-10, par2
     finally:
         S.free()
+
+
+def test_parity_two_ranks(emu_lib, oracle_ref, tmp_path):
+    """The same check with the lattice split along T over two gloo ranks: every rank writes its part, slab j is evaluated by
+    rank j mod 2 from files of both ranks (the halo slices of a slab lie on the other rank), the sums are all-reduced."""
+    import json
+    import socket
+    import subprocess
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs, outs = [], []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   OMP_NUM_THREADS=str(max(1, (os.cpu_count() or 4) // 2)))
+        o = str(tmp_path / ("rank%d.json" % r))
+        outs.append(o)
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "bench_parity_worker.py"), emu_lib, str(tmp_path), o],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = [p.communicate(timeout=900)[0] for p in procs]
+    for p, lg in zip(procs, logs):
+        assert p.returncode == 0, lg[-3000:]
+    res = [json.load(open(o)) for o in outs]
+    for r in res:
+        assert r["iters"] > 0 and r["res"] < 1e-10
+        assert r["parity"].get("ok") is True and r["parity"]["coverage"].startswith("16 of 16"), r
+    assert res[0]["parity"]["residual_ref_operator"] == res[1]["parity"]["residual_ref_operator"]
