@@ -38,7 +38,8 @@ namespace mrhs {
 
 const int NR = 12;                       // right-hand sides
 const int NB = 32;                       // N of the MMA (24 used: [Re | Im], padded to a multiple of 16)
-const int TMEM_COLS = 256;               // 5 accumulators x 32 columns, power of two
+const int TMEM_COLS = 512;               // 5 accumulator sets x 96 columns (see ACC below), power of two
+const int ACC = 96;                      // columns per accumulator set: [hi*hi | hi*lo] (64, one MMA with N = 64) + [lo*hi] (32)
 
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
   // mbarrier wait with a bound: a protocol error traps (CUDA error on the host) instead of hanging the GPU
@@ -160,7 +161,10 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
   };
   if (tid == 0) for (int j = 0; j < STAGES && j < total; j++) issue(j);
 
-  const uint32_t idesc = instr_desc(0, 0, 128, NB);                 // A and B K-major, D = 128 x 32 fp32
+  // A and B K-major.  TF32 x 3 with two MMAs per K step into INDEPENDENT accumulators: A_hi x [B_hi | B_lo] (N = 64: the hi and
+  // lo operand buffers of B are adjacent row groups) and A_lo x B_hi (N = 32), summed in the epilogue.  A chain of dependent
+  // MMAs on one accumulator costs its full latency per link (the first version ran 63 of them back to back per block).
+  const uint32_t idesc64 = instr_desc(0, 0, 128, 2 * NB), idesc32 = instr_desc(0, 0, 128, NB);
   const uint32_t aAfh = smem_u32(Afh), aAfl = smem_u32(Afl), aAdh = smem_u32(Adh), aAdl = smem_u32(Adl);
   const uint32_t aBfh = smem_u32(Bfh), aBfl = smem_u32(Bfl), aBdh = smem_u32(Bdh), aBdl = smem_u32(Bdl);
   uint32_t mma_phase = 0;
@@ -244,14 +248,13 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
       if (tid == 0 && m > 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // daggered: D_mu[c][slot] = sum_rho W[rho][c] B'[slot][rho]; K = 2n, 8 per MMA = two cores (256 B) of A and of B
-        const uint32_t td = tmem + 32u * (uint32_t)m;
+        const uint32_t td = tmem + (uint32_t)(ACC * m);
         for (int ks = 0; ks < n2 / 8; ks++) {
           const uint32_t o = (uint32_t)ks * 256;
           const uint64_t ah = smem_desc(aAdh + o, 128, 4096), al = smem_desc(aAdl + o, 128, 4096);
-          const uint64_t bh = smem_desc(aBdh + o, 128, (uint32_t)kcd * 128), bl = smem_desc(aBdl + o, 128, (uint32_t)kcd * 128);
-          mma_tf32(td, ah, bh, idesc, ks > 0 ? 1u : 0u);
-          mma_tf32(td, al, bh, idesc, 1u);
-          mma_tf32(td, ah, bl, idesc, 1u);
+          const uint64_t bhl = smem_desc(aBdh + o, 128, (uint32_t)kcd * 128);          // rows 0..31 = hi, 32..63 = lo
+          mma_tf32(td, ah, bhl, idesc64, ks > 0 ? 1u : 0u);
+          mma_tf32(td + 64u, al, bhl, idesc32, ks > 0 ? 1u : 0u);
         }
       }
       {
@@ -280,10 +283,9 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
         for (int ks = 0; ks < n / 8; ks++) {
           const uint32_t o = (uint32_t)ks * 256;
           const uint64_t ah = smem_desc(aAfh + o, 128, (uint32_t)kcf * 128), al = smem_desc(aAfl + o, 128, (uint32_t)kcf * 128);
-          const uint64_t bh = smem_desc(aBfh + o, 128, (uint32_t)kcf * 128), bl = smem_desc(aBfl + o, 128, (uint32_t)kcf * 128);
-          mma_tf32(tmem, ah, bh, idesc, (m > 0 || ks > 0) ? 1u : 0u);
-          mma_tf32(tmem, al, bh, idesc, 1u);
-          mma_tf32(tmem, ah, bl, idesc, 1u);
+          const uint64_t bhl = smem_desc(aBfh + o, 128, (uint32_t)kcf * 128);
+          mma_tf32(tmem, ah, bhl, idesc64, (m > 0 || ks > 0) ? 1u : 0u);
+          mma_tf32(tmem + 64u, al, bhl, idesc32, (m > 0 || ks > 0) ? 1u : 0u);
         }
         mma_commit(mma_done);                                        // arrives when every MMA issued so far has completed
       }
@@ -297,9 +299,18 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
     {
       const int row = (warp & 3) * 32 + lane;
       const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-      float v[32];
+      float v[32], v2[32];
+      auto load_sum = [&](uint32_t base) {        // [hi*hi] + [hi*lo] + [lo*hi]
+        tmem_ld32(base, v);
+        tmem_ld32(base + 32u, v2);
+#pragma unroll
+        for (int k = 0; k < 32; k++) v[k] += v2[k];
+        tmem_ld32(base + 64u, v2);
+#pragma unroll
+        for (int k = 0; k < 32; k++) v[k] += v2[k];
+      };
       if (warp < 4) {
-        tmem_ld32(tmem + lane_base, v);
+        load_sum(tmem + lane_base);
         // forward rows rho = 2 r + (re|im): Re Y = P[2r][j] - P[2r+1][12+j], Im Y = P[2r+1][j] + P[2r][12+j]
         const int rho = row, r = rho >> 1, im = rho & 1;
 #pragma unroll
@@ -311,7 +322,7 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
       }
 #pragma unroll 1
       for (int mu = (warp < 4 ? 0 : 2); mu < (warp < 4 ? 2 : 4); mu++) {
-        tmem_ld32(tmem + lane_base + 32u * (uint32_t)(1 + mu), v);
+        load_sum(tmem + lane_base + (uint32_t)(ACC * (1 + mu)));
         const int c = row;
         if (c < n) {
           const float sg = (c < nh) ? 1.f : -1.f;
