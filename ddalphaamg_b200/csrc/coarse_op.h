@@ -42,8 +42,10 @@ bool coarse_sap_mr_fast(const CoarseOp &op, cf *x, const cf *r, const int *d_blo
                         const int *d_jobs, int njobs);
 
 // 12 right-hand sides at once on the tensor cores (sm_100a only; mrhs_kernel.cu): out_j = D_c in_j, vectors j at
-// in + j * vstride; Z: scratch of 12 x zstride complex (zstride >= 4 n V).  Ghost slabs of the inputs must be current.
-bool coarse_apply_mrhs(const CoarseOp &op, cf *out, const cf *in, cf *Z, long vstride, long zstride);
+// in + j * vstride; Z: scratch of 12 x zstride complex (zstride >= 4 n V); T: the operator's MMA-ready images from
+// coarse_mrhs_tile (72 n^2 bytes per site, dev_free() it; rebuild when S / F change).  Ghost slabs of the inputs must be current.
+float *coarse_mrhs_tile(const CoarseOp &op);
+bool coarse_apply_mrhs(const CoarseOp &op, const float *T, cf *out, const cf *in, cf *Z, long vstride, long zstride);
 // even-odd Schur complement of the coarsest operator as streaming kernels (sm_100a only; schur_kernel.cu); vectors are
 // full-lattice arrays in global even-odd order, Z: 4*n complex per site, `skip`: device flag (kernels return if set)
 bool schur_fast_supported(const CoarseOp &op);

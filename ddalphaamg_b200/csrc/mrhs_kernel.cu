@@ -21,12 +21,21 @@
 // fp32 accuracy on TF32 hardware: every operand is split x = hi + lo (hi = 11 significant bits) and each product is three
 // MMAs hi*hi + lo*hi + hi*lo accumulated in the same fp32 TMEM accumulator (error ~2^-21 relative).
 //
-// Per CTA (256 threads, persistent over sites): TMA bulk copies stream the raw blocks into a ring (cp.async.bulk + mbarrier,
-// as in coarse_kernel.cu); all threads re-tile the block (with the hi/lo split) and the right-hand sides into operand
-// buffers; ONE thread issues the tcgen05.mma sequence and commits it to an mbarrier; accumulators live in TMEM (forward:
-// 128 lanes x 32 columns, daggered: 4 x 32 columns) and are read back with tcgen05.ld for the epilogue.  The daggered
-// results go to the scratch field Z and are added at the target sites by k_coarse_combine (scatter form: every hop matrix
-// is read from HBM once per 12 right-hand sides).
+// Operator images.  The operand layouts are fixed by the hardware, the operator is constant over a solve: coarse_mrhs_tile
+// writes, once per operator, every block in the two operand layouts (forward view for S and F_mu, daggered view for F_mu;
+// 9 images of n x n complex per site, 72 n^2 bytes) so that ONE TMA bulk copy per block lands an MMA-ready operand in shared
+// memory.  (The first versions re-tiled the column-major blocks inside the kernel: 45 instructions per matrix element,
+// 1.5 ms per application at 32^3 x 64 against 0.10 ms for one single-RHS application, profiles/r2_ncu_full_k_coarse_mrhs_c.txt.)
+//
+// Per CTA (448 threads, one CTA per SM, persistent over sites), warp-specialised, mbarriers only inside the site loop:
+//   warp 12 (one thread)  producer: cp.async.bulk of block j's image(s) into stage j % STAGES         -> full[stage]
+//   warps 0-7             workers:  B operands of block j (right-hand sides, hi/lo split) into the stage, then the TF32 split
+//                                   of the operator image IN PLACE (hi = truncated value, lo -> second buffer)   -> ready[stage]
+//   warp 13 (one thread)  issuer:   tcgen05.mma sequence of block j, tcgen05.commit                      -> empty[stage], acc_full
+//   warps 8-11            epilogue: tcgen05.ld of the site's five accumulator sets, stores                -> acc_empty
+// Accumulators live in TMEM (forward: 128 lanes x 96 columns, daggered: 4 x 96 columns).  The daggered results go to the
+// scratch field Z and are added at the target sites by k_coarse_combine (scatter form: every hop matrix is read from HBM
+// once per 12 right-hand sides).
 #include "coarse_op.h"
 #include "tma.cuh"
 
@@ -101,98 +110,192 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
   lo = x - hi;
 }
 
-// Operand buffers (floats), all in the canonical no-swizzle K-major layout of tcgen05.mma (verified on the B200 with
+// Operand layouts (floats), all the canonical no-swizzle K-major layout of tcgen05.mma (verified on the B200 with
 // scripts/umma_probe.cu: 128-byte core matrices = 8 rows x 4 K-elements, leading byte offset = distance of the cores
-// adjacent in K, stride byte offset = distance of the 8-row groups):
-//   Af: forward view,  M = rho (16 row groups), K = column c (n/4 cores per row group)      -- the block TRANSPOSED
-//   Ad: daggered view, M = column c (8 row groups of 32 cores), K = rho                     -- the block as it lies in memory
-//   Bf: [Re V | Im V], N = 32 right-hand-side slots (4 row groups), K = c;   Bd: [w | -i w], K = rho
-const int AD_FLOATS = 8 * 32 * 32;
+// adjacent in K, stride byte offset = distance of the 8-row groups).  A block is the real matrix W[rho][c] (rho = 2 r + re|im):
+//   forward image:  M = rho (n/4 row groups), K = c   (n/4 cores per row group)   -- the block TRANSPOSED, 2 n^2 floats
+//   daggered image: M = c   (n/8 row groups), K = rho (n/2 cores per row group)   -- 2 n^2 floats
+//   Bf: [Re V | Im V], N = 32 right-hand-side slots (4 row groups), K = c;   Bd: [w | -i w], K = rho; hi rows 0..31, lo rows 32..63
+// The MMAs run with M = 128: operand rows beyond the image read whatever follows it in shared memory and produce accumulator
+// rows nobody reads (an accumulator row depends on its own operand row only).
+__host__ __device__ inline long fwd_off(int rho, int c, int kcf) { return ((long)(rho >> 3) * kcf + (c >> 2)) * 32 + (rho & 7) * 4 + (c & 3); }
+__host__ __device__ inline long dag_off(int c, int rho, int kcd) { return ((long)(c >> 3) * kcd + (rho >> 2)) * 32 + (c & 7) * 4 + (rho & 3); }
 
-const int NT = 256;                      // threads per CTA (8 warps: re-tiling and operand fills are what the CTA spends its time on)
+// images of site x: [fwd S][fwd F_0, dag F_0] ... [fwd F_3, dag F_3], 18 n^2 floats
+__global__ void __launch_bounds__(256) k_mrhs_tile(CoarseOp op, float *__restrict__ T) {
+  const int n = op.n, n2 = 2 * n, kcf = n / 4, kcd = n / 2, m = blockIdx.y;
+  const long nn = (long)n * n, x = blockIdx.x;
+  const float *W = reinterpret_cast<const float *>(m == 0 ? op.S + x * nn : op.F + (x * 4 + (m - 1)) * nn);
+  float *dst = T + x * 18 * nn + (m == 0 ? 0 : 2 * nn + (long)(m - 1) * 4 * nn);
+  for (int e = threadIdx.x; e < 2 * nn; e += blockDim.x) {
+    const int c = e / n2, rho = e - c * n2;
+    const float v = W[e];
+    dst[fwd_off(rho, c, kcf)] = v;
+    if (m > 0) dst[2 * nn + dag_off(c, rho, kcd)] = v;
+  }
+}
+
+const int NW = 256;                      // worker threads (warps 0-7)
+const int NT = NW + 128 + 64;            // + epilogue warps 8-11 (TMEM lane quarter = warp % 4) + producer warp 12 + issuer warp 13
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
 
 template <int STAGES>
-__global__ void __launch_bounds__(NT)
-k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *__restrict__ Z, long vstride, long zstride, int nsites) {
+__global__ void __launch_bounds__(NT, 1)
+k_coarse_mrhs(CoarseOp op, const float *__restrict__ T, cf *__restrict__ out, const cf *__restrict__ in, cf *__restrict__ Z,
+              long vstride, long zstride, int nsites) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int n = op.n, nn = n * n, nh = n / 2, n2 = 2 * n;
   const int kcf = n / 4, kcd = n2 / 4;                              // K cores of the forward / daggered operands
-  const int AF_FLOATS = 16 * kcf * 32;
-  float *Afh = reinterpret_cast<float *>(smem_raw);
-  float *Afl = Afh + AF_FLOATS;
-  float *Adh = Afl + AF_FLOATS;
-  float *Adl = Adh + AD_FLOATS;
-  float *Bfh = Adl + AD_FLOATS;                                     // [4][kcf][32]
-  float *Bfl = Bfh + 4 * kcf * 32;
-  float *Bdh = Bfl + 4 * kcf * 32;                                  // [4][kcd][32]
-  float *Bdl = Bdh + 4 * kcd * 32;
-  cf *raw = reinterpret_cast<cf *>(Bdl + 4 * kcd * 32);             // [STAGES][nn]
-  uint64_t *full = reinterpret_cast<uint64_t *>(raw + (size_t)STAGES * nn);   // [STAGES]
-  uint64_t *mma_done = full + STAGES;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mma_done + 1);
+  // stage: [hi fwd 2nn][hi dag 2nn][lo fwd 2nn][lo dag 2nn][Bf hi 32n][Bf lo 32n];  then 2 x [Bd hi 64n][Bd lo 64n]
+  const int SF = 8 * nn + 64 * n, BDF = 128 * n;
+  float *stage0 = reinterpret_cast<float *>(smem_raw);
+  float *Bd0 = stage0 + (size_t)STAGES * SF;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + ((size_t)STAGES * SF + 2 * BDF) * sizeof(float) + 8192);   // slack: see above
+  uint64_t *ready = full + STAGES, *empty = ready + STAGES, *acc_full = empty + STAGES, *acc_empty = acc_full + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t bytes = (uint32_t)(nn * sizeof(cf));
   const int my_sites = (nsites - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total = 5 * my_sites;
 
-  for (int q = tid; q < 2 * AF_FLOATS + 2 * AD_FLOATS + 8 * (kcf + kcd) * 32; q += NT) Afh[q] = 0.f;   // padding stays zero
+  for (int q = tid; q < STAGES * SF + 2 * BDF; q += NT) stage0[q] = 0.f;        // unused right-hand-side slots stay zero
   if (tid == 0) {
-    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
-    mbar_init(mma_done, 1);
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&ready[s], NW / 32); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  auto issue = [&](int j) {
-    const int k = j / 5, m = j - 5 * k;
-    const long x = (long)blockIdx.x + (long)k * gridDim.x;
-    const cf *src = (m == 0) ? op.S + x * nn : op.F + (x * 4 + (m - 1)) * nn;
-    const int st = j % STAGES;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&full[st], bytes);
-    tma_bulk_g2s(raw + (size_t)st * nn, src, bytes, &full[st]);
-  };
-  if (tid == 0) for (int j = 0; j < STAGES && j < total; j++) issue(j);
-
-  // A and B K-major.  TF32 x 3 with two MMAs per K step into INDEPENDENT accumulators: A_hi x [B_hi | B_lo] (N = 64: the hi and
-  // lo operand buffers of B are adjacent row groups) and A_lo x B_hi (N = 32), summed in the epilogue.  A chain of dependent
-  // MMAs on one accumulator costs its full latency per link (the first version ran 63 of them back to back per block).
-  const uint32_t idesc64 = instr_desc(0, 0, 128, 2 * NB), idesc32 = instr_desc(0, 0, 128, NB);
-  const uint32_t aAfh = smem_u32(Afh), aAfl = smem_u32(Afl), aAdh = smem_u32(Adh), aAdl = smem_u32(Adl);
-  const uint32_t aBfh = smem_u32(Bfh), aBfl = smem_u32(Bfl), aBdh = smem_u32(Bdh), aBdl = smem_u32(Bdl);
-  uint32_t mma_phase = 0;
-
-  // the right-hand sides a block multiplies (12 x n complex) are fetched one block ahead into registers
-  const int NPRE = 3;                                               // 12 * 64 / NT
-  cf pre[NPRE];
-  auto prefetch = [&](int j) {                                      // vectors of block j: site x (S) or x + mu (F_mu)
-    const int k = j / 5, m = j - 5 * k;
-    const long x = (long)blockIdx.x + (long)k * gridDim.x;
-    const long src = (m == 0) ? x : (long)op.nb[(long)(m - 1) * op.V + x];
-#pragma unroll
-    for (int i = 0; i < NPRE; i++) {
-      const int q = tid + NT * i;
-      if (q < NR * n) { const int jr = q / n, c = q - jr * n; pre[i] = in[(long)jr * vstride + src * n + c]; }
+  if (warp == 12) {
+    // ---------------- producer: one bulk copy per block ----------------
+    if (lane == 0) {
+      for (int j = 0; j < total; j++) {
+        const int k = j / 5, m = j - 5 * k, s = j % STAGES, u = j / STAGES;
+        const long x = (long)blockIdx.x + (long)k * gridDim.x;
+        if (u > 0) mbar_wait_bounded(&empty[s], (uint32_t)((u - 1) & 1));
+        const uint32_t bytes = (uint32_t)((m == 0 ? 2 : 4) * nn * sizeof(float));
+        const float *src = T + x * 18 * (long)nn + (m == 0 ? 0 : 2 * (long)nn + (long)(m - 1) * 4 * nn);
+        mbar_expect_tx(&full[s], bytes);
+        tma_bulk_g2s(stage0 + (size_t)s * SF, src, bytes, &full[s]);
+      }
     }
-  };
-  if (total > 0) prefetch(0);
-
-  for (int k = 0; k < my_sites; k++) {
-    const long x = (long)blockIdx.x + (long)k * gridDim.x;
-    for (int m = 0; m < 5; m++) {
-      const int j = 5 * k + m, st = j % STAGES;
+  } else if (warp == 13) {
+    // ---------------- issuer: A and B K-major.  TF32 x 3 with two MMAs per K step into INDEPENDENT accumulators:
+    // A_hi x [B_hi | B_lo] (N = 64: the hi and lo operand buffers of B are adjacent row groups) and A_lo x B_hi (N = 32),
+    // summed in the epilogue ----------------
+    if (lane == 0) {
+      const uint32_t idesc64 = instr_desc(0, 0, 128, 2 * NB), idesc32 = instr_desc(0, 0, 128, NB);
+      const uint32_t sbf = (uint32_t)kcf * 128, sbd = (uint32_t)kcd * 128;
+      for (int j = 0; j < total; j++) {
+        const int k = j / 5, m = j - 5 * k, s = j % STAGES, u = j / STAGES;
+        mbar_wait_bounded(&ready[s], (uint32_t)(u & 1));
+        if (m == 0 && k > 0) mbar_wait_bounded(acc_empty, (uint32_t)((k - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = smem_u32(stage0 + (size_t)s * SF);
+        const uint32_t aHF = a0, aHD = a0 + 8u * nn, aLF = a0 + 16u * nn, aLD = a0 + 24u * nn, aBf = a0 + 32u * nn;
+        if (m > 0) {
+          // daggered: D_mu[c][slot] = sum_rho W[rho][c] B'[slot][rho]; K = 2n, 8 per MMA = two cores (256 B) of A and of B
+          const uint32_t td = tmem + (uint32_t)(ACC * m), aBd = smem_u32(Bd0 + (size_t)(k & 1) * BDF);
+          for (int ks = 0; ks < n2 / 8; ks++) {
+            const uint32_t o = (uint32_t)ks * 256;
+            const uint64_t ah = smem_desc(aHD + o, 128, sbd), al = smem_desc(aLD + o, 128, sbd), bhl = smem_desc(aBd + o, 128, sbd);
+            mma_tf32(td, ah, bhl, idesc64, ks > 0 ? 1u : 0u);
+            mma_tf32(td + 64u, al, bhl, idesc32, ks > 0 ? 1u : 0u);
+          }
+        }
+        // forward: D_fwd[rho][slot] += sum_c W[rho][c] B[slot][c]; K = n
+        for (int ks = 0; ks < n / 8; ks++) {
+          const uint32_t o = (uint32_t)ks * 256;
+          const uint64_t ah = smem_desc(aHF + o, 128, sbf), al = smem_desc(aLF + o, 128, sbf), bhl = smem_desc(aBf + o, 128, sbf);
+          mma_tf32(tmem, ah, bhl, idesc64, (m > 0 || ks > 0) ? 1u : 0u);
+          mma_tf32(tmem + 64u, al, bhl, idesc32, (m > 0 || ks > 0) ? 1u : 0u);
+        }
+        mma_commit(&empty[s]);                                       // arrives when every MMA issued so far has completed
+        if (m == 4) mma_commit(acc_full);
+      }
+    }
+  } else if (warp >= 8) {
+    // ---------------- epilogue: accumulators -> registers -> global.  A warp reaches the TMEM lanes 32 (warp % 4) .. +31 =
+    // rows of the accumulators ----------------
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+    float v[32], v2[32];
+    auto load_sum = [&](uint32_t base) {        // [hi*hi] + [hi*lo] + [lo*hi]
+      tmem_ld32(base, v);
+      tmem_ld32(base + 32u, v2);
+#pragma unroll
+      for (int q = 0; q < 32; q++) v[q] += v2[q];
+      tmem_ld32(base + 64u, v2);
+#pragma unroll
+      for (int q = 0; q < 32; q++) v[q] += v2[q];
+    };
+    for (int k = 0; k < my_sites; k++) {
+      const long x = (long)blockIdx.x + (long)k * gridDim.x;
+      mbar_wait_bounded(acc_full, (uint32_t)(k & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      load_sum(tmem + lane_base);
+      {
+        // forward rows rho = 2 r + (re|im): Re Y = P[2r][j] - P[2r+1][12+j], Im Y = P[2r+1][j] + P[2r][12+j]
+        const int rho = row, r = rho >> 1, im = rho & 1;
+#pragma unroll
+        for (int j = 0; j < NR; j++) {
+          const float other = __shfl_xor_sync(0xffffffffu, v[NR + j], 1);     // partner row's [12 + j] entry
+          const float val = im ? v[j] + other : v[j] - other;
+          if (rho < n2) reinterpret_cast<float *>(out + (long)j * vstride + x * n + r)[im] = val;
+        }
+      }
+#pragma unroll 1
+      for (int mu = 0; mu < 4; mu++) {
+        load_sum(tmem + lane_base + (uint32_t)(ACC * (1 + mu)));
+        const int c = row;
+        if (c < n) {
+          const float sg = (c < nh) ? 1.f : -1.f;
+#pragma unroll
+          for (int j = 0; j < NR; j++) Z[(long)j * zstride + (x * 4 + mu) * n + c] = cf(sg * v[j], sg * v[NR + j]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);                          // accumulators are free for the next site
+    }
+  } else {
+    // ---------------- workers ----------------
+    // the right-hand sides a block multiplies (12 x n complex) are fetched one block ahead into registers
+    const int NPRE = 3;                                               // 12 * 64 / NW
+    cf pre[NPRE];
+    auto prefetch = [&](int j) {                                      // vectors of block j: site x (S) or x + mu (F_mu)
+      const int k = j / 5, m = j - 5 * k;
+      const long x = (long)blockIdx.x + (long)k * gridDim.x;
+      const long src = (m == 0) ? x : (long)op.nb[(long)(m - 1) * op.V + x];
+#pragma unroll
+      for (int i = 0; i < NPRE; i++) {
+        const int q = tid + NW * i;
+        if (q < NR * n) { const int jr = q / n, c = q - jr * n; pre[i] = in[(long)jr * vstride + src * n + c]; }
+      }
+    };
+    if (total > 0) prefetch(0);
+    for (int j = 0; j < total; j++) {
+      const int k = j / 5, m = j - 5 * k, s = j % STAGES, u = j / STAGES;
+      float *stg = stage0 + (size_t)s * SF;
+      float *Bfh = stg + 8 * nn, *Bfl = Bfh + 32 * n;
+      float *Bdh = Bd0 + (size_t)(k & 1) * BDF, *Bdl = Bdh + 64 * n;
+      if (u > 0) mbar_wait_bounded(&empty[s], (uint32_t)((u - 1) & 1));   // the MMAs that read this stage's B operands (and, in
+                                                                         // order, everything before them) have completed
       // forward B = [Re V | Im V] from the prefetched registers; for m = 0 these are the site's own vectors, from which
       // the daggered operand B' = [w | -i w], w = G5 V(x), is filled as well (rows j and 12 + j, K = rho = 2 r + re|im)
 #pragma unroll
       for (int i = 0; i < NPRE; i++) {
-        const int q = tid + NT * i;
+        const int q = tid + NW * i;
         if (q < NR * n) {
           const int jr = q / n, c = q - jr * n;
           const cf v = pre[i];
@@ -220,122 +323,24 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
         }
       }
       if (j + 1 < total) prefetch(j + 1);
-      mbar_wait_bounded(&full[st], (uint32_t)((j / STAGES) & 1));
-      // re-tile the raw block (column-major complex = real W[rho][c], rho fastest) in two passes, each followed by its MMAs, so
-      // that the tensor core works on the daggered product while the threads build the forward operand:
-      //   pass 1, daggered view: 16-byte chunk (column c, rho = 4g..4g+3) -> core matrix (c / 8, g), row c % 8   (one 16-byte store)
-      //   pass 2, forward view:  element (rho, c) -> core (rho / 8, c / 4), row rho % 8, position c % 4          (four scalar stores)
-      // lanes: c % 4 = lane % 4, g % 2 = (lane / 4) % 2, and in store step t lane group r = lane / 8 writes rho = 4 g + (t + r) % 4:
-      // the 32 lanes of a scalar store hit 32 distinct banks (the first version of this kernel lost 71 % of its shared-memory
-      // wavefronts to conflicts here, profiles/r2_ncu_full_k_coarse_mrhs_a.txt)
-      const float4 *R4 = reinterpret_cast<const float4 *>(raw + (size_t)st * nn);
-      const int ncq = n >> 2, ngq = kcd >> 1, combos = ncq * ngq;
-      if (m > 0) {
-        for (int u = warp * 4 + (lane >> 3); u < combos; u += 4 * (NT / 32)) {
-          const int cq = u / ngq, gq = u - cq * ngq;
-          const int c = 4 * cq + (lane & 3), g = 2 * gq + ((lane >> 2) & 1);
-          const float4 v = R4[c * kcd + g];
-          float4 h, l;
-          split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-          const int od = ((c >> 3) * 32 + g) * 32 + (c & 7) * 4;
-          *reinterpret_cast<float4 *>(Adh + od) = h;
-          *reinterpret_cast<float4 *>(Adl + od) = l;
-        }
+      mbar_wait_bounded(&full[s], (uint32_t)(u & 1));
+      // TF32 split of the image(s) in place: hi = value truncated to 11 significant bits, lo = value - hi
+      float4 *H4 = reinterpret_cast<float4 *>(stg), *L4 = H4 + nn;
+      const int cnt = (m == 0 ? nn : 2 * nn) / 2;                        // float4 elements
+      for (int i = tid; i < cnt; i += NW) {
+        const float4 v = H4[i];
+        float4 h, l;
+        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+        H4[i] = h; L4[i] = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // operand buffers written by the generic proxy
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      if (tid == 0 && m > 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // daggered: D_mu[c][slot] = sum_rho W[rho][c] B'[slot][rho]; K = 2n, 8 per MMA = two cores (256 B) of A and of B
-        const uint32_t td = tmem + (uint32_t)(ACC * m);
-        for (int ks = 0; ks < n2 / 8; ks++) {
-          const uint32_t o = (uint32_t)ks * 256;
-          const uint64_t ah = smem_desc(aAdh + o, 128, 4096), al = smem_desc(aAdl + o, 128, 4096);
-          const uint64_t bhl = smem_desc(aBdh + o, 128, (uint32_t)kcd * 128);          // rows 0..31 = hi, 32..63 = lo
-          mma_tf32(td, ah, bhl, idesc64, ks > 0 ? 1u : 0u);
-          mma_tf32(td + 64u, al, bhl, idesc32, ks > 0 ? 1u : 0u);
-        }
-      }
-      {
-        const int r = lane >> 3;
-        for (int u = warp * 4 + r; u < combos; u += 4 * (NT / 32)) {
-          const int cq = u / ngq, gq = u - cq * ngq;
-          const int c = 4 * cq + (lane & 3), g = 2 * gq + ((lane >> 2) & 1);
-          const float4 v = R4[c * kcd + g];
-#pragma unroll
-          for (int t = 0; t < 4; t++) {
-            const int tt = (t + r) & 3;
-            const float x = tt == 0 ? v.x : (tt == 1 ? v.y : (tt == 2 ? v.z : v.w));
-            float hi, lo; split_tf32(x, hi, lo);
-            const int rho = 4 * g + tt;
-            const int of = ((rho >> 3) * kcf + (c >> 2)) * 32 + (rho & 7) * 4 + (c & 3);
-            Afh[of] = hi; Afl[of] = lo;
-          }
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // forward: D_fwd[rho][slot] += sum_c W[rho][c] B[slot][c]; K = n
-        for (int ks = 0; ks < n / 8; ks++) {
-          const uint32_t o = (uint32_t)ks * 256;
-          const uint64_t ah = smem_desc(aAfh + o, 128, (uint32_t)kcf * 128), al = smem_desc(aAfl + o, 128, (uint32_t)kcf * 128);
-          const uint64_t bhl = smem_desc(aBfh + o, 128, (uint32_t)kcf * 128);
-          mma_tf32(tmem, ah, bhl, idesc64, (m > 0 || ks > 0) ? 1u : 0u);
-          mma_tf32(tmem + 64u, al, bhl, idesc32, (m > 0 || ks > 0) ? 1u : 0u);
-        }
-        mma_commit(mma_done);                                        // arrives when every MMA issued so far has completed
-      }
-      mbar_wait_bounded(mma_done, mma_phase & 1);                    // operand buffers and the raw stage are free again
-      mma_phase++;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (tid == 0 && j + STAGES < total) issue(j + STAGES);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ready[s]);
     }
-    // epilogue: accumulators -> registers -> global.  A warp reaches the TMEM lanes 32 (warp % 4) .. +31 = rows of the
-    // accumulators; warps 0-3 take the forward accumulator and the daggered ones of mu = 0, 1, warps 4-7 those of mu = 2, 3.
-    {
-      const int row = (warp & 3) * 32 + lane;
-      const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-      float v[32], v2[32];
-      auto load_sum = [&](uint32_t base) {        // [hi*hi] + [hi*lo] + [lo*hi]
-        tmem_ld32(base, v);
-        tmem_ld32(base + 32u, v2);
-#pragma unroll
-        for (int k = 0; k < 32; k++) v[k] += v2[k];
-        tmem_ld32(base + 64u, v2);
-#pragma unroll
-        for (int k = 0; k < 32; k++) v[k] += v2[k];
-      };
-      if (warp < 4) {
-        load_sum(tmem + lane_base);
-        // forward rows rho = 2 r + (re|im): Re Y = P[2r][j] - P[2r+1][12+j], Im Y = P[2r+1][j] + P[2r][12+j]
-        const int rho = row, r = rho >> 1, im = rho & 1;
-#pragma unroll
-        for (int j = 0; j < NR; j++) {
-          const float other = __shfl_xor_sync(0xffffffffu, v[NR + j], 1);     // partner row's [12 + j] entry
-          const float val = im ? v[j] + other : v[j] - other;
-          if (rho < n2) reinterpret_cast<float *>(out + (long)j * vstride + x * n + r)[im] = val;
-        }
-      }
-#pragma unroll 1
-      for (int mu = (warp < 4 ? 0 : 2); mu < (warp < 4 ? 2 : 4); mu++) {
-        load_sum(tmem + lane_base + (uint32_t)(ACC * (1 + mu)));
-        const int c = row;
-        if (c < n) {
-          const float sg = (c < nh) ? 1.f : -1.f;
-#pragma unroll
-          for (int j = 0; j < NR; j++) Z[(long)j * zstride + (x * 4 + mu) * n + c] = cf(sg * v[j], sg * v[NR + j]);
-        }
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();                                                 // accumulators are free for the next site
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TMEM_COLS));
 }
 
@@ -343,24 +348,41 @@ k_coarse_mrhs(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, cf *
 
 void coarse_combine(const CoarseOp &op, cf *out, const cf *in, const cf *Z);   // coarse_kernel.cu: eta(x) += sum_mu Z[x-mu][mu]
 
+bool coarse_mrhs_supported(const CoarseOp &op) { return !(op.n > 64 || op.n < 8 || (op.n & 7) || op.V <= 0); }
+
+// operator images of the 12-RHS kernel (72 n^2 bytes per site); rebuild after every change of op.S / op.F.  dev_free() it.
+float *coarse_mrhs_tile(const CoarseOp &op) {
+  if (!coarse_mrhs_supported(op)) return nullptr;
+  float *T = dev_alloc<float>((size_t)op.V * 18 * op.n * op.n);
+  mrhs::k_mrhs_tile<<<dim3((unsigned)op.V, 5), 256, 0, g_stream>>>(op, T);
+  g_launch_count++;
+  CUDA_CHECK(cudaGetLastError());
+  return T;
+}
+
 // out_j = D_c in_j for j < 12: vectors j at in + j * vstride / out + j * vstride (vstride >= (V + ghost sites) * n), Z: scratch
-// of 12 x zstride complex (zstride >= 4 n V).  Halo slabs of the inputs must be current.  Returns false when the shape is
-// not supported.
-bool coarse_apply_mrhs(const CoarseOp &op, cf *out, const cf *in, cf *Z, long vstride, long zstride) {
+// of 12 x zstride complex (zstride >= 4 n V), T: coarse_mrhs_tile(op).  Halo slabs of the inputs must be current.  Returns
+// false when the shape is not supported.
+bool coarse_apply_mrhs(const CoarseOp &op, const float *T, cf *out, const cf *in, cf *Z, long vstride, long zstride) {
   const int n = op.n;
-  if (n > 64 || n < 8 || (n & 7) || op.V <= 0) return false;
+  if (!coarse_mrhs_supported(op) || !T) return false;
   const size_t nn = (size_t)n * n;
-  const int STAGES = 2;
-  const size_t smem = (2 * (size_t)(16 * (n / 4) * 32) + 2 * (size_t)mrhs::AD_FLOATS + 8 * (size_t)(n / 4 + n / 2) * 32) * sizeof(float) +
-                      STAGES * nn * sizeof(cf) + (STAGES + 1) * sizeof(uint64_t) + 16;
-  static size_t attr = 0;
-  if (smem > attr) { CUDA_CHECK(cudaFuncSetAttribute(mrhs::k_coarse_mrhs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  auto need = [&](int stages) { return ((size_t)stages * (8 * nn + 64 * n) + 256 * (size_t)n) * sizeof(float) + 8192 + (3 * stages + 2) * sizeof(uint64_t) + 16; };
+  const size_t limit = 226 * 1024;                              // 227 KB per CTA minus the kernel's static shared memory
+  const int stages = need(2) <= limit ? 2 : 1;
+  const size_t smem = need(stages);
+  if (smem > limit) return false;
+  static size_t attr[3] = {0, 0, 0};
   static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  const int per_sm = (int)std::min<size_t>(2, (227 * 1024) / (smem + 1024));    // TMEM: 2 x 256 columns per SM
-  if (per_sm < 1) return false;
-  const long grid = std::min<long>(op.V, (long)sms * per_sm);
-  mrhs::k_coarse_mrhs<2><<<(unsigned)grid, mrhs::NT, smem, g_stream>>>(op, out, in, Z, vstride, zstride, (int)op.V);
+  if (!sms) sms = dev_sm_count();
+  const long grid = std::min<long>(op.V, (long)sms);                 // one CTA per SM: the CTA owns all 512 TMEM columns
+  if (stages == 2) {
+    if (smem > attr[2]) { CUDA_CHECK(cudaFuncSetAttribute(mrhs::k_coarse_mrhs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[2] = smem; }
+    mrhs::k_coarse_mrhs<2><<<(unsigned)grid, mrhs::NT, smem, g_stream>>>(op, T, out, in, Z, vstride, zstride, (int)op.V);
+  } else {
+    if (smem > attr[1]) { CUDA_CHECK(cudaFuncSetAttribute(mrhs::k_coarse_mrhs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[1] = smem; }
+    mrhs::k_coarse_mrhs<1><<<(unsigned)grid, mrhs::NT, smem, g_stream>>>(op, T, out, in, Z, vstride, zstride, (int)op.V);
+  }
   g_launch_count++;
   for (int j = 0; j < mrhs::NR; j++) coarse_combine(op, out + (long)j * vstride, in + (long)j * vstride, Z + (long)j * zstride);
 #ifdef DDA_DEBUG_SYNC

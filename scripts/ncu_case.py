@@ -29,8 +29,8 @@ def main():
         for d in (1, 2):
             V, nc = S.level_shape(d)
             vs = (rng.standard_normal((12, V * nc)) + 1j * rng.standard_normal((12, V * nc))).astype(np.complex64)
-            o, ms = S.level_apply_mrhs(d, vs, reps=3)
-            print("mrhs depth", d, "ms per 12-RHS apply", ms, "single", S.bench_op(BENCH.LEVEL_APPLY, d, 3))
+            o, ms = S.level_apply_mrhs(d, vs, reps=10)
+            print("mrhs depth", d, "ms per 12-RHS apply", ms, "single", S.bench_op(BENCH.LEVEL_APPLY, d, 10))
         S.free()
         return
     if case == "sap":
