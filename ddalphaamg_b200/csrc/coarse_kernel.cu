@@ -158,6 +158,35 @@ void coarse_combine(const CoarseOp &op, cf *out, const cf *in, const cf *Z) {
   k_coarse_combine<<<(unsigned)((total + 127) / 128), 128, 0, g_stream>>>(op, out, in, Z, total);
   g_launch_count++;
 }
+// the same for nrhs vectors in one launch (vector j at out + j * vstride, in + j * vstride, Z + j * zstride)
+__global__ void k_coarse_combine_batch(CoarseOp op, cf *__restrict__ out, const cf *__restrict__ in, const cf *__restrict__ Z, long total,
+                                       long vstride, long zstride) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = op.n, nh = n / 2;
+  const long x = i / n; const int r = (int)(i - x * n);
+  const long nn = (long)n * n;
+  out += blockIdx.y * vstride; in += blockIdx.y * vstride; Z += blockIdx.y * zstride;
+  cf acc = out[i];
+#pragma unroll
+  for (int mu = 0; mu < 4; mu++) {
+    const long nbr = op.nb[(long)(4 + mu) * op.V + x];
+    if (nbr < op.V) acc += Z[(nbr * 4 + mu) * n + r];
+    else {
+      const cf *M = op.F + (nbr * 4 + mu) * nn + (long)r * n, *v = in + nbr * n;
+      cf a1(0.f, 0.f), a2(0.f, 0.f);
+      for (int c = 0; c < nh; c++) fmac_(a1, M[c], v[c]);
+      for (int c = nh; c < n; c++) fmac_(a2, M[c], v[c]);
+      acc += (r < nh) ? (a1 - a2) : (a2 - a1);
+    }
+  }
+  out[i] = acc;
+}
+void coarse_combine_batch(const CoarseOp &op, cf *out, const cf *in, const cf *Z, int nrhs, long vstride, long zstride) {
+  const long total = op.V * op.n;
+  k_coarse_combine_batch<<<dim3((unsigned)((total + 127) / 128), (unsigned)nrhs), 128, 0, g_stream>>>(op, out, in, Z, total, vstride, zstride);
+  g_launch_count++;
+}
 
 // -------------------------------------------------------------------------------------------------------------------
 // Fused SAP block solve on an intermediate level: ONE CTA per Schwarz block runs all block_iter minimal-residual steps

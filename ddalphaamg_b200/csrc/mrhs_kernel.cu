@@ -28,14 +28,21 @@
 // 1.5 ms per application at 32^3 x 64 against 0.10 ms for one single-RHS application, profiles/r2_ncu_full_k_coarse_mrhs_c.txt.)
 //
 // Per CTA (448 threads, one CTA per SM, persistent over sites), warp-specialised, mbarriers only inside the site loop:
-//   warp 12 (one thread)  producer: cp.async.bulk of block j's image(s) into stage j % STAGES         -> full[stage]
-//   warps 0-7             workers:  B operands of block j (right-hand sides, hi/lo split) into the stage, then the TF32 split
-//                                   of the operator image IN PLACE (hi = truncated value, lo -> second buffer)   -> ready[stage]
+//   warp 12 (one thread)  producer: cp.async.bulk of block j's image(s) into landing buffer j % 2          -> full[stage]
+//   warps 0-7             workers (two groups of four warps, group g owns the blocks j = g mod 2): B operands of block j
+//                                   (right-hand sides, hi/lo split), then the TF32 split of the landed image into operand set
+//                                   j % 2 (hi = truncated value, lo = remainder)               -> ready[stage], rawfree[stage]
 //   warp 13 (one thread)  issuer:   tcgen05.mma sequence of block j, tcgen05.commit                      -> empty[stage], acc_full
 //   warps 8-11            epilogue: tcgen05.ld of the site's five accumulator sets, stores                -> acc_empty
-// Accumulators live in TMEM (forward: 128 lanes x 96 columns, daggered: 4 x 96 columns).  The daggered results go to the
-// scratch field Z and are added at the target sites by k_coarse_combine (scatter form: every hop matrix is read from HBM
-// once per 12 right-hand sides).
+// (for n > 40 the landing buffers do not fit next to two operand sets: the copies land in the operand set and are split in
+// place; for n >= 56 there is one operand set.)  Accumulators live in TMEM (forward: 128 lanes x 96 columns, daggered: 4 x 96
+// columns).  The daggered results go to the scratch field Z and are added at the target sites by k_coarse_combine_batch
+// (scatter form: every hop matrix is read from HBM once per 12 right-hand sides).
+//
+// Measured (B200, 32^3 x 64 level 1: 8 192 sites, n = 40): 0.47 ms per 12-RHS application against 12 x 0.10 ms single-RHS
+// applications (2.6 x); profiles/r2_ncu_full_k_coarse_mrhs_d.txt.  What bounds it now is shared-memory bandwidth: per block the
+// tensor core reads 165 KB of operands (M = 128 rows per MMA although only 2n = 80 / n = 40 are occupied, hi and lo images
+// read for separate MMAs) and the split adds 100 KB, against 25.6 KB of HBM traffic; tensor pipe 24 % active, DRAM 32 %.
 #include "coarse_op.h"
 #include "tma.cuh"
 
@@ -50,13 +57,16 @@ const int NB = 32;                       // N of the MMA (24 used: [Re | Im], pa
 const int TMEM_COLS = 512;               // 5 accumulator sets x 96 columns (see ACC below), power of two
 const int ACC = 96;                      // columns per accumulator set: [hi*hi | hi*lo] (64, one MMA with N = 64) + [lo*hi] (32)
 
+template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
-  // mbarrier wait with a bound: a protocol error traps (CUDA error on the host) instead of hanging the GPU
+  // mbarrier wait with a bound: a protocol error traps (CUDA error on the host) instead of hanging the GPU.  BACKOFF: roles
+  // that wait for a whole block / site sleep between polls and leave the issue slots to the worker warps.
   for (long it = 0; it < (1L << 26); it++) {
     uint32_t ok;
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     if (ok) return;
+    if (BACKOFF) __nanosleep(64);
   }
   __trap();
 }
@@ -135,6 +145,22 @@ __global__ void __launch_bounds__(256) k_mrhs_tile(CoarseOp op, float *__restric
   }
 }
 
+// shared-memory layout (bytes): STAGES operand sets [hi fwd 2nn][hi dag 2nn][lo fwd 2nn][lo dag 2nn][Bf hi 32n][Bf lo 32n] (floats),
+// 2 x [Bd hi 64n][Bd lo 64n], RAW landing buffers of 4nn floats (RAW = 0: the bulk copies land in the hi buffers of the operand
+// set and are split in place), slack for the M = 128 reads past the last daggered image, mbarriers
+struct Layout { size_t stage_f, bd_f, raw_f, bar_off, total; };
+__host__ __device__ inline Layout layout(int n, int stages, int raw) {
+  Layout L;
+  const size_t nn = (size_t)n * n;
+  L.stage_f = 8 * nn + 64 * (size_t)n; L.bd_f = 128 * (size_t)n; L.raw_f = 4 * nn;
+  const size_t bytes = (stages * L.stage_f + 2 * L.bd_f + raw * L.raw_f) * sizeof(float);
+  const size_t overrun = (size_t)(16 - n / 8) * 64 * n, following = (64 * (size_t)n + 2 * L.bd_f + raw * L.raw_f) * sizeof(float);
+  const size_t slack = overrun > following ? ((overrun - following + 127) / 128) * 128 : 0;
+  L.bar_off = bytes + slack;
+  L.total = L.bar_off + 10 * sizeof(uint64_t) + 16;
+  return L;
+}
+
 const int NW = 256;                      // worker threads (warps 0-7)
 const int NT = NW + 128 + 64;            // + epilogue warps 8-11 (TMEM lane quarter = warp % 4) + producer warp 12 + issuer warp 13
 
@@ -142,7 +168,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
-template <int STAGES>
+template <int STAGES, int RAW>
 __global__ void __launch_bounds__(NT, 1)
 k_coarse_mrhs(CoarseOp op, const float *__restrict__ T, cf *__restrict__ out, const cf *__restrict__ in, cf *__restrict__ Z,
               long vstride, long zstride, int nsites) {
@@ -150,19 +176,24 @@ k_coarse_mrhs(CoarseOp op, const float *__restrict__ T, cf *__restrict__ out, co
   const int n = op.n, nn = n * n, nh = n / 2, n2 = 2 * n;
   const int kcf = n / 4, kcd = n2 / 4;                              // K cores of the forward / daggered operands
   // stage: [hi fwd 2nn][hi dag 2nn][lo fwd 2nn][lo dag 2nn][Bf hi 32n][Bf lo 32n];  then 2 x [Bd hi 64n][Bd lo 64n]
-  const int SF = 8 * nn + 64 * n, BDF = 128 * n;
+  const Layout lay = layout(n, STAGES, RAW);
+  const int SF = (int)lay.stage_f, BDF = (int)lay.bd_f, RF = (int)lay.raw_f;
   float *stage0 = reinterpret_cast<float *>(smem_raw);
   float *Bd0 = stage0 + (size_t)STAGES * SF;
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + ((size_t)STAGES * SF + 2 * BDF) * sizeof(float) + 8192);   // slack: see above
-  uint64_t *ready = full + STAGES, *empty = ready + STAGES, *acc_full = empty + STAGES, *acc_empty = acc_full + 1;
+  float *raw0 = Bd0 + 2 * (size_t)BDF;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + lay.bar_off);
+  uint64_t *ready = full + 2, *empty = ready + 2, *rawfree = empty + 2, *acc_full = rawfree + 2, *acc_empty = acc_full + 1;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int my_sites = (nsites - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total = 5 * my_sites;
 
   for (int q = tid; q < STAGES * SF + 2 * BDF; q += NT) stage0[q] = 0.f;        // unused right-hand-side slots stay zero
+  static_assert(RAW == 0 || RAW == STAGES, "landing buffers are owned by the worker group of the same index");
   if (tid == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&ready[s], NW / 32); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full[s], 1); mbar_init(&ready[s], NW / STAGES / 32); mbar_init(&empty[s], 1); mbar_init(&rawfree[s], NW / STAGES / 32);
+    }
     mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -182,11 +213,13 @@ k_coarse_mrhs(CoarseOp op, const float *__restrict__ T, cf *__restrict__ out, co
       for (int j = 0; j < total; j++) {
         const int k = j / 5, m = j - 5 * k, s = j % STAGES, u = j / STAGES;
         const long x = (long)blockIdx.x + (long)k * gridDim.x;
-        if (u > 0) mbar_wait_bounded(&empty[s], (uint32_t)((u - 1) & 1));
+        // the landing buffer is free: RAW: the workers have split its previous block into the operand set; in place: the MMAs
+        // that read the operand set have completed
+        if (u > 0) mbar_wait_bounded<true>(RAW ? &rawfree[s] : &empty[s], (uint32_t)((u - 1) & 1));
         const uint32_t bytes = (uint32_t)((m == 0 ? 2 : 4) * nn * sizeof(float));
         const float *src = T + x * 18 * (long)nn + (m == 0 ? 0 : 2 * (long)nn + (long)(m - 1) * 4 * nn);
         mbar_expect_tx(&full[s], bytes);
-        tma_bulk_g2s(stage0 + (size_t)s * SF, src, bytes, &full[s]);
+        tma_bulk_g2s(RAW ? raw0 + (size_t)s * RF : stage0 + (size_t)s * SF, src, bytes, &full[s]);
       }
     }
   } else if (warp == 13) {
@@ -201,24 +234,25 @@ k_coarse_mrhs(CoarseOp op, const float *__restrict__ T, cf *__restrict__ out, co
         mbar_wait_bounded(&ready[s], (uint32_t)(u & 1));
         if (m == 0 && k > 0) mbar_wait_bounded(acc_empty, (uint32_t)((k - 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // descriptors: the start-address field counts 16-byte units, a K step of 8 (two cores, 256 bytes) adds 16 to it
         const uint32_t a0 = smem_u32(stage0 + (size_t)s * SF);
-        const uint32_t aHF = a0, aHD = a0 + 8u * nn, aLF = a0 + 16u * nn, aLD = a0 + 24u * nn, aBf = a0 + 32u * nn;
         if (m > 0) {
-          // daggered: D_mu[c][slot] = sum_rho W[rho][c] B'[slot][rho]; K = 2n, 8 per MMA = two cores (256 B) of A and of B
-          const uint32_t td = tmem + (uint32_t)(ACC * m), aBd = smem_u32(Bd0 + (size_t)(k & 1) * BDF);
-          for (int ks = 0; ks < n2 / 8; ks++) {
-            const uint32_t o = (uint32_t)ks * 256;
-            const uint64_t ah = smem_desc(aHD + o, 128, sbd), al = smem_desc(aLD + o, 128, sbd), bhl = smem_desc(aBd + o, 128, sbd);
+          // daggered: D_mu[c][slot] = sum_rho W[rho][c] B'[slot][rho]; K = 2n
+          const uint32_t td = tmem + (uint32_t)(ACC * m);
+          uint64_t ah = smem_desc(a0 + 8u * nn, 128, sbd), al = smem_desc(a0 + 24u * nn, 128, sbd);
+          uint64_t bhl = smem_desc(smem_u32(Bd0 + (size_t)(k & 1) * BDF), 128, sbd);
+          for (int ks = 0; ks < n2 / 8; ks++, ah += 16, al += 16, bhl += 16) {
             mma_tf32(td, ah, bhl, idesc64, ks > 0 ? 1u : 0u);
             mma_tf32(td + 64u, al, bhl, idesc32, ks > 0 ? 1u : 0u);
           }
         }
         // forward: D_fwd[rho][slot] += sum_c W[rho][c] B[slot][c]; K = n
-        for (int ks = 0; ks < n / 8; ks++) {
-          const uint32_t o = (uint32_t)ks * 256;
-          const uint64_t ah = smem_desc(aHF + o, 128, sbf), al = smem_desc(aLF + o, 128, sbf), bhl = smem_desc(aBf + o, 128, sbf);
-          mma_tf32(tmem, ah, bhl, idesc64, (m > 0 || ks > 0) ? 1u : 0u);
-          mma_tf32(tmem + 64u, al, bhl, idesc32, (m > 0 || ks > 0) ? 1u : 0u);
+        {
+          uint64_t ah = smem_desc(a0, 128, sbf), al = smem_desc(a0 + 16u * nn, 128, sbf), bhl = smem_desc(a0 + 32u * nn, 128, sbf);
+          for (int ks = 0; ks < n / 8; ks++, ah += 16, al += 16, bhl += 16) {
+            mma_tf32(tmem, ah, bhl, idesc64, (m > 0 || ks > 0) ? 1u : 0u);
+            mma_tf32(tmem + 64u, al, bhl, idesc32, (m > 0 || ks > 0) ? 1u : 0u);
+          }
         }
         mma_commit(&empty[s]);                                       // arrives when every MMA issued so far has completed
         if (m == 4) mma_commit(acc_full);
@@ -241,7 +275,7 @@ k_coarse_mrhs(CoarseOp op, const float *__restrict__ T, cf *__restrict__ out, co
     };
     for (int k = 0; k < my_sites; k++) {
       const long x = (long)blockIdx.x + (long)k * gridDim.x;
-      mbar_wait_bounded(acc_full, (uint32_t)(k & 1));
+      mbar_wait_bounded<true>(acc_full, (uint32_t)(k & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       load_sum(tmem + lane_base);
       {
@@ -269,23 +303,45 @@ k_coarse_mrhs(CoarseOp op, const float *__restrict__ T, cf *__restrict__ out, co
       if (lane == 0) mbar_arrive(acc_empty);                          // accumulators are free for the next site
     }
   } else {
-    // ---------------- workers ----------------
-    // the right-hand sides a block multiplies (12 x n complex) are fetched one block ahead into registers
-    const int NPRE = 3;                                               // 12 * 64 / NW
+    // ---------------- workers: STAGES groups of NW / STAGES threads, group g owns stage g = the blocks j = g (mod STAGES), so
+    // that the latency chains of consecutive blocks (wait, global loads, shared-memory round trips) overlap ----------------
+    const int NWG = NW / STAGES, NPRE = (16 * 64 + NWG - 1) / NWG;
+    const int g = tid / NWG, gt = tid - g * NWG;
+    // a thread's right-hand-side elements: slot q = gt + NWG i -> (jr, c) with c % 4 = q % 4 and jr % 8 = (q / 4) % 8, i.e. the 32
+    // lanes of a warp store to 32 distinct banks of the core-matrix layout (8 rows x 4 K-elements).  Offsets are per thread
+    // constants: element offset in a vector, operand offsets of Re (row jr) / Im (row 12 + jr) in Bf and of the two rows in Bd.
+    long voff[NPRE]; int o0[NPRE], o1[NPRE], d0[NPRE], d1[NPRE]; bool hi_half[NPRE];
+#pragma unroll
+    for (int i = 0; i < NPRE; i++) {
+      const int q = gt + NWG * i, rest = q >> 5;
+      const int jr = (rest & 1) * 8 + ((q >> 2) & 7), c = (rest >> 1) * 4 + (q & 3);
+      const bool ok = jr < NR && c < n;
+      const int row1 = NR + jr, kk = 2 * c;
+      voff[i] = ok ? (long)jr * vstride + c : -1;
+      o0[i] = ((jr >> 3) * kcf + (c >> 2)) * 32 + (jr & 7) * 4 + (c & 3);
+      o1[i] = ((row1 >> 3) * kcf + (c >> 2)) * 32 + (row1 & 7) * 4 + (c & 3);
+      d0[i] = ((jr >> 3) * kcd + (kk >> 2)) * 32 + (jr & 7) * 4 + (kk & 3);
+      d1[i] = ((row1 >> 3) * kcd + (kk >> 2)) * 32 + (row1 & 7) * 4 + (kk & 3);
+      hi_half[i] = c >= nh;
+    }
+    // the right-hand sides a block multiplies (12 x n complex) are fetched one block of this group ahead into registers, the
+    // neighbour index two ahead
     cf pre[NPRE];
-    auto prefetch = [&](int j) {                                      // vectors of block j: site x (S) or x + mu (F_mu)
+    auto source = [&](int j) -> int {                                // vectors of block j: site x (S) or x + mu (F_mu)
       const int k = j / 5, m = j - 5 * k;
       const long x = (long)blockIdx.x + (long)k * gridDim.x;
-      const long src = (m == 0) ? x : (long)op.nb[(long)(m - 1) * op.V + x];
-#pragma unroll
-      for (int i = 0; i < NPRE; i++) {
-        const int q = tid + NW * i;
-        if (q < NR * n) { const int jr = q / n, c = q - jr * n; pre[i] = in[(long)jr * vstride + src * n + c]; }
-      }
+      return (m == 0) ? (int)x : __ldg(op.nb + (long)(m - 1) * op.V + x);
     };
-    if (total > 0) prefetch(0);
-    for (int j = 0; j < total; j++) {
-      const int k = j / 5, m = j - 5 * k, s = j % STAGES, u = j / STAGES;
+    auto prefetch = [&](int src) {
+#pragma unroll
+      for (int i = 0; i < NPRE; i++)
+        if (voff[i] >= 0) pre[i] = in[voff[i] + (long)src * n];
+    };
+    int src_next = 0;
+    if (g < total) prefetch(source(g));
+    if (g + STAGES < total) src_next = source(g + STAGES);
+    for (int j = g; j < total; j += STAGES) {
+      const int k = j / 5, m = j - 5 * k, s = g, u = j / STAGES;
       float *stg = stage0 + (size_t)s * SF;
       float *Bfh = stg + 8 * nn, *Bfl = Bfh + 32 * n;
       float *Bdh = Bd0 + (size_t)(k & 1) * BDF, *Bdl = Bdh + 64 * n;
@@ -295,47 +351,52 @@ k_coarse_mrhs(CoarseOp op, const float *__restrict__ T, cf *__restrict__ out, co
       // the daggered operand B' = [w | -i w], w = G5 V(x), is filled as well (rows j and 12 + j, K = rho = 2 r + re|im)
 #pragma unroll
       for (int i = 0; i < NPRE; i++) {
-        const int q = tid + NW * i;
-        if (q < NR * n) {
-          const int jr = q / n, c = q - jr * n;
+        if (voff[i] >= 0) {
           const cf v = pre[i];
-          const int row1 = NR + jr;
-          const int o0 = ((jr >> 3) * kcf + (c >> 2)) * 32 + (jr & 7) * 4 + (c & 3);
-          const int o1 = ((row1 >> 3) * kcf + (c >> 2)) * 32 + (row1 & 7) * 4 + (c & 3);
           float hi, lo;
-          split_tf32(v.re, hi, lo); Bfh[o0] = hi; Bfl[o0] = lo;
-          split_tf32(v.im, hi, lo); Bfh[o1] = hi; Bfl[o1] = lo;
+          split_tf32(v.re, hi, lo); Bfh[o0[i]] = hi; Bfl[o0[i]] = lo;
+          split_tf32(v.im, hi, lo); Bfh[o1[i]] = hi; Bfl[o1[i]] = lo;
           if (m == 0) {
-            const cf w = (c >= nh) ? -v : v;
-            const float val[2][2] = {{w.re, w.im}, {w.im, -w.re}};   // [row block][re | im position]
-#pragma unroll
-            for (int blk = 0; blk < 2; blk++) {
-              const int row = blk * NR + jr;
-#pragma unroll
-              for (int ri = 0; ri < 2; ri++) {
-                const int kk = 2 * c + ri;
-                const int o = ((row >> 3) * kcd + (kk >> 2)) * 32 + (row & 7) * 4 + (kk & 3);
-                split_tf32(val[blk][ri], hi, lo);
-                Bdh[o] = hi; Bdl[o] = lo;
-              }
-            }
+            const cf w = hi_half[i] ? -v : v;
+            split_tf32(w.re, hi, lo);  Bdh[d0[i]] = hi;     Bdl[d0[i]] = lo;        // row jr:      [ w.re,  w.im ]
+            split_tf32(w.im, hi, lo);  Bdh[d0[i] + 1] = hi; Bdl[d0[i] + 1] = lo;
+            Bdh[d1[i]] = hi;           Bdl[d1[i]] = lo;                             // row 12 + jr: [ w.im, -w.re ]
+            split_tf32(-w.re, hi, lo); Bdh[d1[i] + 1] = hi; Bdl[d1[i] + 1] = lo;
           }
         }
       }
-      if (j + 1 < total) prefetch(j + 1);
+      if (j + STAGES < total) {
+        prefetch(src_next);
+        if (j + 2 * STAGES < total) src_next = source(j + 2 * STAGES);
+      }
       mbar_wait_bounded(&full[s], (uint32_t)(u & 1));
-      // TF32 split of the image(s) in place: hi = value truncated to 11 significant bits, lo = value - hi
+      // TF32 split of the image(s) into the operand set (RAW = 0: in place): hi = value truncated to 11 significant bits,
+      // lo = value - hi
       float4 *H4 = reinterpret_cast<float4 *>(stg), *L4 = H4 + nn;
+      const float4 *R4 = RAW ? reinterpret_cast<const float4 *>(raw0 + (size_t)s * RF) : H4;
       const int cnt = (m == 0 ? nn : 2 * nn) / 2;                        // float4 elements
-      for (int i = tid; i < cnt; i += NW) {
-        const float4 v = H4[i];
+      int i = gt;
+      for (; i + 3 * NWG < cnt; i += 4 * NWG) {                          // four independent load -> split -> store chains
+        float4 v[4], h[4], l[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) v[t] = R4[i + t * NWG];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          split_tf32(v[t].x, h[t].x, l[t].x); split_tf32(v[t].y, h[t].y, l[t].y);
+          split_tf32(v[t].z, h[t].z, l[t].z); split_tf32(v[t].w, h[t].w, l[t].w);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++) { H4[i + t * NWG] = h[t]; L4[i + t * NWG] = l[t]; }
+      }
+      for (; i < cnt; i += NWG) {
+        const float4 v = R4[i];
         float4 h, l;
         split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
         H4[i] = h; L4[i] = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // operand buffers written by the generic proxy
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ready[s]);
+      if (lane == 0) { mbar_arrive(&ready[s]); if (RAW) mbar_arrive(&rawfree[s]); }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -346,7 +407,8 @@ k_coarse_mrhs(CoarseOp op, const float *__restrict__ T, cf *__restrict__ out, co
 
 }  // namespace mrhs
 
-void coarse_combine(const CoarseOp &op, cf *out, const cf *in, const cf *Z);   // coarse_kernel.cu: eta(x) += sum_mu Z[x-mu][mu]
+// coarse_kernel.cu: eta_j(x) += sum_mu Z_j[x-mu][mu] for nrhs vectors in one launch
+void coarse_combine_batch(const CoarseOp &op, cf *out, const cf *in, const cf *Z, int nrhs, long vstride, long zstride);
 
 bool coarse_mrhs_supported(const CoarseOp &op) { return !(op.n > 64 || op.n < 8 || (op.n & 7) || op.V <= 0); }
 
@@ -366,25 +428,29 @@ float *coarse_mrhs_tile(const CoarseOp &op) {
 bool coarse_apply_mrhs(const CoarseOp &op, const float *T, cf *out, const cf *in, cf *Z, long vstride, long zstride) {
   const int n = op.n;
   if (!coarse_mrhs_supported(op) || !T) return false;
-  const size_t nn = (size_t)n * n;
-  auto need = [&](int stages) { return ((size_t)stages * (8 * nn + 64 * n) + 256 * (size_t)n) * sizeof(float) + 8192 + (3 * stages + 2) * sizeof(uint64_t) + 16; };
-  const size_t limit = 226 * 1024;                              // 227 KB per CTA minus the kernel's static shared memory
-  const int stages = need(2) <= limit ? 2 : 1;
-  const size_t smem = need(stages);
-  if (smem > limit) return false;
+  // configurations: two operand sets + two landing buffers (n <= 40), two operand sets split in place (n = 48), one (n >= 56)
+  const size_t limit = 226 * 1024;                                   // 227 KB per CTA minus the kernel's static shared memory
+  int cfg = -1;
+  const int stages_of[3] = {2, 2, 1}, raw_of[3] = {2, 0, 0};
+  for (int c = 0; c < 3 && cfg < 0; c++)
+    if (mrhs::layout(n, stages_of[c], raw_of[c]).total <= limit) cfg = c;
+  static const char *force = getenv("DDA_MRHS_CONFIG");              // A/B runs: 0, 1, 2
+  if (force && atoi(force) > cfg && atoi(force) < 3) cfg = atoi(force);
+  if (cfg < 0) return false;
+  const size_t smem = mrhs::layout(n, stages_of[cfg], raw_of[cfg]).total;
   static size_t attr[3] = {0, 0, 0};
   static int sms = 0;
   if (!sms) sms = dev_sm_count();
   const long grid = std::min<long>(op.V, (long)sms);                 // one CTA per SM: the CTA owns all 512 TMEM columns
-  if (stages == 2) {
-    if (smem > attr[2]) { CUDA_CHECK(cudaFuncSetAttribute(mrhs::k_coarse_mrhs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[2] = smem; }
-    mrhs::k_coarse_mrhs<2><<<(unsigned)grid, mrhs::NT, smem, g_stream>>>(op, T, out, in, Z, vstride, zstride, (int)op.V);
-  } else {
-    if (smem > attr[1]) { CUDA_CHECK(cudaFuncSetAttribute(mrhs::k_coarse_mrhs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[1] = smem; }
-    mrhs::k_coarse_mrhs<1><<<(unsigned)grid, mrhs::NT, smem, g_stream>>>(op, T, out, in, Z, vstride, zstride, (int)op.V);
-  }
+  auto launch = [&](auto kern) {
+    if (smem > attr[cfg]) { CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[cfg] = smem; }
+    kern<<<(unsigned)grid, mrhs::NT, smem, g_stream>>>(op, T, out, in, Z, vstride, zstride, (int)op.V);
+  };
+  if (cfg == 0) launch(mrhs::k_coarse_mrhs<2, 2>);
+  else if (cfg == 1) launch(mrhs::k_coarse_mrhs<2, 0>);
+  else launch(mrhs::k_coarse_mrhs<1, 0>);
   g_launch_count++;
-  for (int j = 0; j < mrhs::NR; j++) coarse_combine(op, out + (long)j * vstride, in + (long)j * vstride, Z + (long)j * zstride);
+  coarse_combine_batch(op, out, in, Z, mrhs::NR, vstride, zstride);
 #ifdef DDA_DEBUG_SYNC
   CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaGetLastError());
 #endif
