@@ -465,6 +465,26 @@ def run_native(args, w, name):
     schur_ms = S.bench_op(BENCH.COARSEST_SCHUR, nlev - 1, 50)
     add("coarsest_schur_n%d" % ncl, schur_ms, Vl_solve * (2 * 4 + 1) * ncl * ncl * 8.0)
 
+    # ---- 12 right-hand sides through the tensor-core kernel (single rank: the entry point takes whole-lattice
+    # vectors).  Checked against the single-RHS kernel on one column, timed next to 12 single-RHS applications.
+    tensor_core = None
+    if world == 1 and nlev > 1:
+        rng = np.random.default_rng(5)
+        Vc, nc = S.level_shape(1)
+        vs = (rng.standard_normal((12, Vc * nc)) + 1j * rng.standard_normal((12, Vc * nc))).astype(np.complex64)
+        o12, ms12 = S.level_apply_mrhs(1, vs, reps=reps)
+        one = S.level_apply(1, vs[5])
+        single_ms = ops["coarse_apply_d1_n%d" % nc]["ms"]
+        tb = 9 * nc * nc * 8.0 * Vc + 12 * 2 * nc * 8.0 * Vc            # operator images once + 12 vectors in and out
+        fl = 12 * 9 * 8.0 * nc * nc * Vc                                # complex multiply-adds of 9 blocks x 12 columns
+        tensor_core = {"kernel": "mrhs::k_coarse_mrhs: D_c on 12 right-hand sides, tcgen05.mma kind::tf32 (TF32x3 split), TMEM accumulators",
+                       "depth": 1, "n": nc, "sites": Vc, "ms_per_12rhs_apply": ms12, "ms_single_rhs_apply": single_ms,
+                       "speedup_vs_12_single_rhs_applies": 12 * single_ms / ms12,
+                       "relerr_column5_vs_single_rhs_kernel": float(np.linalg.norm(o12[5] - one) / np.linalg.norm(one)),
+                       "algorithmic_bytes": tb, "gbs": tb / (ms12 * 1e-3) / 1e9, "frac_of_peak": tb / (ms12 * 1e-3) / 1e9 / peak,
+                       "fp32_equivalent_tflops": fl / (ms12 * 1e-3) / 1e12}
+        del vs, o12, one
+
     torch.cuda.profiler.stop()
 
     # ---- time shares of one profiled solve (device-synchronising timers per operator class)
@@ -595,6 +615,8 @@ def run_native(args, w, name):
            "time_share_seconds_profiled_solve": share, "wall_seconds_timed_region": wall}
     if target is not None:
         out["target_64c128"] = target
+    if tensor_core is not None:
+        out["tensor_core_12rhs"] = tensor_core
 
     if rank == 0 and world == 1 and not args.no_cpu:
         # the reference runs in its own process (it aborts the process on any error, main.h:424-439)
