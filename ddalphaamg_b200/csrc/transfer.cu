@@ -60,7 +60,15 @@ void tr_chirality_part(const Transfer &t, cf *v, const cf *src, int ch) {
 // Orthonormalise vecs[0..nv) per aggregate and per chirality.  Classical Gram-Schmidt applied twice per vector
 // (numerically equivalent to the reference's modified Gram-Schmidt, linalg_generic.c:400-454); all coefficients stay
 // on the device, no host synchronisation.
+bool tr_gram_schmidt_fast(const Transfer &t, cf *const *vecs);   // transfer_kernel.cu: CholeskyQR2, one CTA per (aggregate, chirality)
+
 void tr_gram_schmidt_aggregates(const Transfer &t, cf *const *vecs, double *scratch) {
+#ifndef DDA_HOST_EMU
+  {
+    const char *e = getenv("DDA_GS_FAST");                         // A/B switch, read per call (tests compare both paths)
+    if (g_transfer_fast && !(e && atoi(e) == 0) && tr_gram_schmidt_fast(t, vecs)) return;
+  }
+#endif
   const int nv = t.nv, h = t.nc / 2, as = t.as;
   const Lay lay = t.lay;
   VecPtrs vp;
