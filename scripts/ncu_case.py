@@ -33,6 +33,14 @@ def main():
             print("mrhs depth", d, "ms per 12-RHS apply", ms, "single", S.bench_op(BENCH.LEVEL_APPLY, d, 10))
         S.free()
         return
+    if case == "galerkin":
+        # setup kernels (fused Galerkin construction, aggregate orthonormalisation) on 32^3x64: capture with -k regex:<kernel>
+        S = DDalphaAMG(lat, [4, 4, 4, 4], levels=3, test_vectors=(20, 28), setup_iter=(0, 0), restart=10, m0=-0.35, csw=1.0,
+                       mixed_precision=2, coarse_block=[2, 2, 2, 2])
+        S.set_conf(random_gauge_field(lat, seed=20261018, eps=0.3))
+        S.setup(0)
+        S.free()
+        return
     if case == "sapmr48":
         # level-1 SAP block solves at the benchmark size (24 x 12^3 coarse lattice, 3x2x2x2 blocks: 864 blocks per launch)
         lat = [96, 48, 48, 48]
