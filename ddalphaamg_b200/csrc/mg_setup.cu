@@ -269,7 +269,8 @@ void mg_setup(Solver &s, int setup_iters) {
     }
   }
   if (p.method <= 0 || p.num_levels < 2) { s.nlev = 1; s.setup_done = true; return; }
-  mg_alloc(s);
+  const double t_begin = now_s();
+  { SetupTimer st_(5); mg_alloc(s); }
   double m_solve = s.m0_op;
   if (p.setup_m0 != s.m0_op) solver_shift_mass(s, p.setup_m0);
   for (int d = 0; d + 1 < s.nlev; d++) {
@@ -290,8 +291,8 @@ void mg_setup(Solver &s, int setup_iters) {
   if (m_solve != s.m0_op) solver_shift_mass(s, m_solve);
   dev_sync();
   if (g_setup_profile) {
-    fprintf(stderr, "dd_alpha_amg_b200 setup phases [s]: test-vector smoothing %.3f, aggregate Gram-Schmidt %.3f, Galerkin %.3f, bootstrap cycles %.3f (nested levels included), global Gram-Schmidt %.3f\n",
-            g_t_setup[0], g_t_setup[1], g_t_setup[2], g_t_setup[3], g_t_setup[4]);
+    fprintf(stderr, "dd_alpha_amg_b200 setup phases [s]: test-vector smoothing %.3f, aggregate Gram-Schmidt %.3f, Galerkin %.3f, bootstrap cycles %.3f (nested levels included), global Gram-Schmidt %.3f, level allocation %.3f, total %.3f\n",
+            g_t_setup[0], g_t_setup[1], g_t_setup[2], g_t_setup[3], g_t_setup[4], g_t_setup[5], now_s() - t_begin);
     for (double &t : g_t_setup) t = 0;
   }
 }
