@@ -44,6 +44,10 @@ static void build_transfer(Level &L, Level &N) {
 void mg_alloc(Solver &s) {
   const Params &p = s.p;
   s.nlev = p.num_levels;
+  double t_mark = now_s();
+  auto mark = [&](const char *what) {
+    if (g_setup_profile) { const double t = now_s(); fprintf(stderr, "dd_alpha_amg_b200 mg_alloc: %s %.3f s\n", what, t - t_mark); t_mark = t; }
+  };
   for (int d = 0; d < s.nlev; d++) {
     Level &L = s.lev[d];
     L.depth = d; L.last = (d == s.nlev - 1);
@@ -68,6 +72,7 @@ void mg_alloc(Solver &s) {
       L.copZ = dev_alloc<cf>(g.V * 4 * c.n);
     }
   }
+  mark("coarse geometries and operators");
   for (int d = 0; d < s.nlev; d++) {
     Level &L = s.lev[d];
     const long n = L.geo.valloc();
@@ -95,7 +100,9 @@ void mg_alloc(Solver &s) {
       L.kc.prec = [sp, dd](cf *out, const cf *in) { mg_vcycle(*sp, dd, out, in, true); };
     }
   }
+  mark("level vectors");
   coarsest_alloc(s);     // coarsest-level solver (device-resident GMRES, gathered lattice when the level is partitioned)
+  mark("coarsest solver");
 }
 
 void mg_free(Solver &s) {
