@@ -143,7 +143,8 @@ void mg_rebuild_coarse(Solver &s, int depth) {
   if (depth == 0 && s.use_fast && g_galerkin_fast) {
     // fused construction (galerkin_kernel.cu): all columns in one launch, no intermediate vectors
     for (int k = 0; k < nv; k++) lv_halo(L, L.P[k]);
-    done = galerkin_fine_fast(L.opf, L.tr, c.S, c.F);
+    // (4^4 aggregates: the kernel maps the four +mu faces of 64 sites onto its 256 threads)
+    if (L.geo.A[0] == 4 && L.geo.A[1] == 4 && L.geo.A[2] == 4 && L.geo.A[3] == 4) done = galerkin_fine_fast(L.opf, L.tr, c.S, c.F);
   }
 #endif
   for (int j = 0; j < n && !done; j++) {
