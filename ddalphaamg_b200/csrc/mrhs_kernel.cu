@@ -40,9 +40,11 @@
 // (scatter form: every hop matrix is read from HBM once per 12 right-hand sides).
 //
 // Measured (B200, 32^3 x 64 level 1: 8 192 sites, n = 40): 0.47 ms per 12-RHS application against 12 x 0.10 ms single-RHS
-// applications (2.6 x); profiles/r2_ncu_full_k_coarse_mrhs_d.txt.  What bounds it now is shared-memory bandwidth: per block the
-// tensor core reads 165 KB of operands (M = 128 rows per MMA although only 2n = 80 / n = 40 are occupied, hi and lo images
-// read for separate MMAs) and the split adds 100 KB, against 25.6 KB of HBM traffic; tensor pipe 24 % active, DRAM 32 %.
+// applications (2.6 x); profiles/r2_ncu_full_k_coarse_mrhs_d.txt: tensor pipe 24 % active, DRAM 32 %, shared-memory pipe ~80 %
+// busy (per block the tensor core reads 165 KB of operands, M = 128 rows per MMA although only 2n = 80 / n = 40 are occupied,
+// and the split adds 100 KB, against 25.6 KB of HBM traffic).  An experiment with the operand roles swapped (right-hand sides
+// as the M = 64 operand: 110 KB of operand reads) ran at the same speed (profiles/RESULTS_r2.md), so the bound is the
+// per-block hand-off chain and the 30 MMAs issued by one thread, not shared-memory bandwidth.
 #include "coarse_op.h"
 #include "tma.cuh"
 
@@ -53,18 +55,9 @@ namespace dda {
 namespace mrhs {
 
 const int NR = 12;                       // right-hand sides
-const int TMEM_COLS = 512;               // accumulator set = 2n (forward) + 4 n (daggered) columns; two sets when 12 n <= 512
-
-// Operand roles.  The RIGHT-HAND SIDES are the M operand (M = 64), the operator images the N operand (N = 2n rows of the
-// forward image, n rows of the daggered one): an MMA then reads 64 x 8 + N x 8 operand elements from shared memory instead
-// of 128 x 8 (most rows padding) + 64 x 8 with the roles the other way round, and shared-memory bandwidth is what bounds the
-// kernel.  TF32 x 3: operand rows hold hi and lo parts of the right-hand sides, and every K step issues two MMAs into the
-// SAME accumulator, [V_hi; V_lo] x W_hi and [V_hi; V_lo] x W_lo; the epilogue adds the V_hi and V_lo rows
-// (V_lo x W_lo, 2^-22 relative, is a legitimate term of the exact product).
-// Rows of the M = 64 operand: r = 16 q + t, q = right-hand side / 3, jj = right-hand side % 3; with M = 64 the accumulator
-// row r lives in TMEM lane 32 q + t, i.e. epilogue warp q finds the hi / lo and Re / Im rows of its three right-hand sides
-// in its own lanes:  t = (jj + 2q) % 8 (+ 3: Im row; + 8: lo part); the rotation by 2q spreads the operand fill over the banks.
-__host__ __device__ inline int row_low(int q, int jj, int im) { return (jj + 3 * im + 2 * q) & 7; }
+const int NB = 32;                       // N of the MMA (24 used: [Re | Im], padded to a multiple of 16)
+const int TMEM_COLS = 512;               // 5 accumulator sets x 96 columns (see ACC below), power of two
+const int ACC = 96;                      // columns per accumulator set: [hi*hi | hi*lo] (64, one MMA with N = 64) + [lo*hi] (32)
 
 template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
@@ -124,28 +117,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
   for (int k = 0; k < 32; k++) v[k] = __uint_as_float(r[k]);
 }
 
-// 32 lanes x 16 columns -> 16 registers per thread, issue and wait separated (the wait names the registers, so that no use of
-// them is scheduled before it)
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float *v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
-                 "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]) : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld16_wait(float *v) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
-                 "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]) :: "memory");
-}
-// 32 lanes x 8 columns -> 8 registers per thread
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int k = 0; k < 8; k++) v[k] = __uint_as_float(r[k]);
-}
-
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   lo = x - hi;
@@ -156,7 +127,9 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
 // adjacent in K, stride byte offset = distance of the 8-row groups).  A block is the real matrix W[rho][c] (rho = 2 r + re|im):
 //   forward image:  M = rho (n/4 row groups), K = c   (n/4 cores per row group)   -- the block TRANSPOSED, 2 n^2 floats
 //   daggered image: M = c   (n/8 row groups), K = rho (n/2 cores per row group)   -- 2 n^2 floats
-//   Af: rows Re V_j / Im V_j (hi and lo parts), M = 64 (8 row groups), K = c;   Ad: rows [w | -i w], w = G5 V_j(x), K = rho
+//   Bf: [Re V | Im V], N = 32 right-hand-side slots (4 row groups), K = c;   Bd: [w | -i w], K = rho; hi rows 0..31, lo rows 32..63
+// The MMAs run with M = 128: operand rows beyond the image read whatever follows it in shared memory and produce accumulator
+// rows nobody reads (an accumulator row depends on its own operand row only).
 __host__ __device__ inline long fwd_off(int rho, int c, int kcf) { return ((long)(rho >> 3) * kcf + (c >> 2)) * 32 + (rho & 7) * 4 + (c & 3); }
 __host__ __device__ inline long dag_off(int c, int rho, int kcd) { return ((long)(c >> 3) * kcd + (rho >> 2)) * 32 + (c & 7) * 4 + (rho & 3); }
 
@@ -176,15 +149,17 @@ __global__ void __launch_bounds__(256) k_mrhs_tile(CoarseOp op, float *__restric
 
 // shared-memory layout (bytes): STAGES operand sets [hi fwd 2nn][hi dag 2nn][lo fwd 2nn][lo dag 2nn][Bf hi 32n][Bf lo 32n] (floats),
 // 2 x [Bd hi 64n][Bd lo 64n], RAW landing buffers of 4nn floats (RAW = 0: the bulk copies land in the hi buffers of the operand
-// set and are split in place), mbarriers
+// set and are split in place), slack for the M = 128 reads past the last daggered image, mbarriers
 struct Layout { size_t stage_f, bd_f, raw_f, bar_off, total; };
 __host__ __device__ inline Layout layout(int n, int stages, int raw) {
   Layout L;
   const size_t nn = (size_t)n * n;
   L.stage_f = 8 * nn + 64 * (size_t)n; L.bd_f = 128 * (size_t)n; L.raw_f = 4 * nn;
   const size_t bytes = (stages * L.stage_f + 2 * L.bd_f + raw * L.raw_f) * sizeof(float);
-  L.bar_off = bytes;                                                  // M and N of the MMAs are exact: no reads past an operand
-  L.total = L.bar_off + 16 * sizeof(uint64_t) + 16;
+  const size_t overrun = (size_t)(16 - n / 8) * 64 * n, following = (64 * (size_t)n + 2 * L.bd_f + raw * L.raw_f) * sizeof(float);
+  const size_t slack = overrun > following ? ((overrun - following + 127) / 128) * 128 : 0;
+  L.bar_off = bytes + slack;
+  L.total = L.bar_off + 10 * sizeof(uint64_t) + 16;
   return L;
 }
 
@@ -195,7 +170,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
-template <int STAGES, int RAW, int GROUPS>
+template <int STAGES, int RAW>
 __global__ void __launch_bounds__(NT, 1)
 k_coarse_mrhs(CoarseOp op, const float *__restrict__ T, cf *__restrict__ out, const cf *__restrict__ in, cf *__restrict__ Z,
               long vstride, long zstride, int nsites) {
@@ -209,20 +184,19 @@ k_coarse_mrhs(CoarseOp op, const float *__restrict__ T, cf *__restrict__ out, co
   float *Bd0 = stage0 + (size_t)STAGES * SF;
   float *raw0 = Bd0 + 2 * (size_t)BDF;
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + lay.bar_off);
-  uint64_t *ready = full + 3, *empty = ready + 3, *rawfree = empty + 3, *acc_full = rawfree + 3, *acc_empty = acc_full + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-  const int asets = (12 * n <= TMEM_COLS) ? 2 : 1;                    // accumulator sets (epilogue of site k overlaps the MMAs of k + 1)
+  uint64_t *ready = full + 2, *empty = ready + 2, *rawfree = empty + 2, *acc_full = rawfree + 2, *acc_empty = acc_full + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int my_sites = (nsites - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total = 5 * my_sites;
 
   for (int q = tid; q < STAGES * SF + 2 * BDF; q += NT) stage0[q] = 0.f;        // unused right-hand-side slots stay zero
-  static_assert((RAW == 0 || RAW == STAGES) && STAGES <= 3, "landing buffer j % RAW feeds operand set j % STAGES");
+  static_assert(RAW == 0 || RAW == STAGES, "landing buffers are owned by the worker group of the same index");
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(&full[s], 1); mbar_init(&ready[s], NW / GROUPS / 32); mbar_init(&empty[s], 1); mbar_init(&rawfree[s], NW / GROUPS / 32);
+      mbar_init(&full[s], 1); mbar_init(&ready[s], NW / STAGES / 32); mbar_init(&empty[s], 1); mbar_init(&rawfree[s], NW / STAGES / 32);
     }
-    for (int q = 0; q < 2; q++) { mbar_init(&acc_full[q], 1); mbar_init(&acc_empty[q], 4); }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -251,125 +225,105 @@ k_coarse_mrhs(CoarseOp op, const float *__restrict__ T, cf *__restrict__ out, co
       }
     }
   } else if (warp == 13) {
-    // ---------------- issuer: operands K-major; per K step [V_hi; V_lo] x W_hi and [V_hi; V_lo] x W_lo into one accumulator --------
+    // ---------------- issuer: A and B K-major.  TF32 x 3 with two MMAs per K step into INDEPENDENT accumulators:
+    // A_hi x [B_hi | B_lo] (N = 64: the hi and lo operand buffers of B are adjacent row groups) and A_lo x B_hi (N = 32),
+    // summed in the epilogue ----------------
     if (lane == 0) {
-      const uint32_t idescF = instr_desc(0, 0, 64, n2), idescD = instr_desc(0, 0, 64, n);
+      const uint32_t idesc64 = instr_desc(0, 0, 128, 2 * NB), idesc32 = instr_desc(0, 0, 128, NB);
       const uint32_t sbf = (uint32_t)kcf * 128, sbd = (uint32_t)kcd * 128;
       for (int j = 0; j < total; j++) {
         const int k = j / 5, m = j - 5 * k, s = j % STAGES, u = j / STAGES;
-        const int aset = k % asets, ause = k / asets;
         mbar_wait_bounded(&ready[s], (uint32_t)(u & 1));
-        if (m == 0 && ause > 0) mbar_wait_bounded(&acc_empty[aset], (uint32_t)((ause - 1) & 1));
+        if (m == 0 && k > 0) mbar_wait_bounded(acc_empty, (uint32_t)((k - 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // descriptors: the start-address field counts 16-byte units, a K step of 8 (two cores, 256 bytes) adds 16 to it
         const uint32_t a0 = smem_u32(stage0 + (size_t)s * SF);
-        const uint32_t tacc = tmem + (uint32_t)(aset * (TMEM_COLS / 2));
         if (m > 0) {
-          // daggered: D_mu[row][c] = sum_rho B'[row][rho] W[rho][c]; K = 2n
-          const uint32_t td = tacc + (uint32_t)(n2 + (m - 1) * n);
-          uint64_t av = smem_desc(smem_u32(Bd0 + (size_t)(k & 1) * BDF), 128, sbd);
-          uint64_t wh = smem_desc(a0 + 8u * nn, 128, sbd), wl = smem_desc(a0 + 24u * nn, 128, sbd);
-          for (int ks = 0; ks < n2 / 8; ks++, av += 16, wh += 16, wl += 16) {
-            mma_tf32(td, av, wh, idescD, ks > 0 ? 1u : 0u);
-            mma_tf32(td, av, wl, idescD, 1u);
+          // daggered: D_mu[c][slot] = sum_rho W[rho][c] B'[slot][rho]; K = 2n
+          const uint32_t td = tmem + (uint32_t)(ACC * m);
+          uint64_t ah = smem_desc(a0 + 8u * nn, 128, sbd), al = smem_desc(a0 + 24u * nn, 128, sbd);
+          uint64_t bhl = smem_desc(smem_u32(Bd0 + (size_t)(k & 1) * BDF), 128, sbd);
+          for (int ks = 0; ks < n2 / 8; ks++, ah += 16, al += 16, bhl += 16) {
+            mma_tf32(td, ah, bhl, idesc64, ks > 0 ? 1u : 0u);
+            mma_tf32(td + 64u, al, bhl, idesc32, ks > 0 ? 1u : 0u);
           }
         }
-        // forward: D_fwd[row][rho] += sum_c V[row][c] W[rho][c]; K = n
+        // forward: D_fwd[rho][slot] += sum_c W[rho][c] B[slot][c]; K = n
         {
-          uint64_t av = smem_desc(a0 + 32u * nn, 128, sbf);
-          uint64_t wh = smem_desc(a0, 128, sbf), wl = smem_desc(a0 + 16u * nn, 128, sbf);
-          for (int ks = 0; ks < n / 8; ks++, av += 16, wh += 16, wl += 16) {
-            mma_tf32(tacc, av, wh, idescF, (m > 0 || ks > 0) ? 1u : 0u);
-            mma_tf32(tacc, av, wl, idescF, 1u);
+          uint64_t ah = smem_desc(a0, 128, sbf), al = smem_desc(a0 + 16u * nn, 128, sbf), bhl = smem_desc(a0 + 32u * nn, 128, sbf);
+          for (int ks = 0; ks < n / 8; ks++, ah += 16, al += 16, bhl += 16) {
+            mma_tf32(tmem, ah, bhl, idesc64, (m > 0 || ks > 0) ? 1u : 0u);
+            mma_tf32(tmem + 64u, al, bhl, idesc32, (m > 0 || ks > 0) ? 1u : 0u);
           }
         }
         mma_commit(&empty[s]);                                       // arrives when every MMA issued so far has completed
-        if (m == 4) mma_commit(&acc_full[aset]);
+        if (m == 4) mma_commit(acc_full);
       }
     }
   } else if (warp >= 8) {
-    // ---------------- epilogue: accumulators -> registers -> global.  Warp q = warp % 4 reaches TMEM lanes 32 q .. 32 q + 31;
-    // with M = 64 the rows 16 q .. 16 q + 15 of the accumulators are its lanes 0 .. 15: lane t < 8 the hi rows, t + 8 the lo rows
-    const int q = warp & 3;
-    const uint32_t lane_base = ((uint32_t)(q * 32)) << 16;
-    const int jj = (lane - 2 * q) & 7;                                // lane = Re row of right-hand side 3 q + jj (if jj < 3)
-    const bool owner = lane < 8 && jj < 3;
-    const int im_lane = (lane + 3) & 7;                               // Im row of the same right-hand side
-    const int jrhs = 3 * q + (jj < 3 ? jj : 0);
+    // ---------------- epilogue: accumulators -> registers -> global.  A warp reaches the TMEM lanes 32 (warp % 4) .. +31 =
+    // rows of the accumulators ----------------
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+    float v[32], v2[32];
+    auto load_sum = [&](uint32_t base) {        // [hi*hi] + [hi*lo] + [lo*hi]
+      tmem_ld32(base, v);
+      tmem_ld32(base + 32u, v2);
+#pragma unroll
+      for (int q = 0; q < 32; q++) v[q] += v2[q];
+      tmem_ld32(base + 64u, v2);
+#pragma unroll
+      for (int q = 0; q < 32; q++) v[q] += v2[q];
+    };
     for (int k = 0; k < my_sites; k++) {
       const long x = (long)blockIdx.x + (long)k * gridDim.x;
-      const int aset = k % asets, ause = k / asets;
-      mbar_wait_bounded<true>(&acc_full[aset], (uint32_t)(ause & 1));
+      mbar_wait_bounded<true>(acc_full, (uint32_t)(k & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem + lane_base + (uint32_t)(aset * (TMEM_COLS / 2));
-      // the 2n forward and 4n daggered columns are one contiguous range, in TMEM and in memory (Z[(4 x + mu) n + c]); 16 columns
-      // per tcgen05.ld, the next load in flight while a chunk is processed.
-      //   forward, columns rho = 2 r + (re|im):  Re Y_r = D[Re][2r] - D[Im][2r+1],  Im Y_r = D[Re][2r+1] + D[Im][2r]
-      //   daggered:                               Z_mu[c] = G5 (D[Re][c], D[Im][c])
-      const int ncol = 6 * n;
-      auto process = [&](float *v, int c0) {
-        float sIm[16];
+      load_sum(tmem + lane_base);
+      {
+        // forward rows rho = 2 r + (re|im): Re Y = P[2r][j] - P[2r+1][12+j], Im Y = P[2r+1][j] + P[2r][12+j]
+        const int rho = row, r = rho >> 1, im = rho & 1;
 #pragma unroll
-        for (int i = 0; i < 16; i++) v[i] += __shfl_down_sync(0xffffffffu, v[i], 8);       // hi + lo rows
-#pragma unroll
-        for (int i = 0; i < 16; i++) sIm[i] = __shfl_sync(0xffffffffu, v[i], im_lane);
-        if (!owner) return;
-        if (c0 < n2) {
-          float4 *dst = reinterpret_cast<float4 *>(out + (long)jrhs * vstride + x * n + (c0 >> 1));
-#pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            dst[i >> 2] = make_float4(v[i] - sIm[i + 1], v[i + 1] + sIm[i], v[i + 2] - sIm[i + 3], v[i + 3] + sIm[i + 2]);
-        } else {
-          const int cc = c0 - n2;
-          int cm = cc % n;                                                                  // component inside its direction
-          float4 *dst = reinterpret_cast<float4 *>(Z + (long)jrhs * zstride + x * 4 * n + cc);
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float s0 = (cm < nh) ? 1.f : -1.f;
-            cm++; if (cm == n) cm = 0;
-            const float s1 = (cm < nh) ? 1.f : -1.f;
-            cm++; if (cm == n) cm = 0;
-            dst[i >> 1] = make_float4(s0 * v[i], s0 * sIm[i], s1 * v[i + 1], s1 * sIm[i + 1]);
-          }
+        for (int j = 0; j < NR; j++) {
+          const float other = __shfl_xor_sync(0xffffffffu, v[NR + j], 1);     // partner row's [12 + j] entry
+          const float val = im ? v[j] + other : v[j] - other;
+          if (rho < n2) reinterpret_cast<float *>(out + (long)j * vstride + x * n + r)[im] = val;
         }
-      };
-      float va[16], vb[16];
-      tmem_ld16_issue(tacc, va);
-      for (int c0 = 0; c0 < ncol; c0 += 32) {
-        tmem_ld16_wait(va);
-        if (c0 + 16 < ncol) tmem_ld16_issue(tacc + (uint32_t)(c0 + 16), vb);
-        process(va, c0);
-        if (c0 + 16 < ncol) {
-          tmem_ld16_wait(vb);
-          if (c0 + 32 < ncol) tmem_ld16_issue(tacc + (uint32_t)(c0 + 32), va);
-          process(vb, c0 + 16);
+      }
+#pragma unroll 1
+      for (int mu = 0; mu < 4; mu++) {
+        load_sum(tmem + lane_base + (uint32_t)(ACC * (1 + mu)));
+        const int c = row;
+        if (c < n) {
+          const float sg = (c < nh) ? 1.f : -1.f;
+#pragma unroll
+          for (int j = 0; j < NR; j++) Z[(long)j * zstride + (x * 4 + mu) * n + c] = cf(sg * v[j], sg * v[NR + j]);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[aset]);                   // this accumulator set is free again
+      if (lane == 0) mbar_arrive(acc_empty);                          // accumulators are free for the next site
     }
   } else {
-    // ---------------- workers: GROUPS groups of NW / GROUPS threads, group g owns the blocks j = g (mod GROUPS), so
+    // ---------------- workers: STAGES groups of NW / STAGES threads, group g owns stage g = the blocks j = g (mod STAGES), so
     // that the latency chains of consecutive blocks (wait, global loads, shared-memory round trips) overlap ----------------
-    const int NWG = NW / GROUPS, NPRE = (16 * 64 + NWG - 1) / NWG;
+    const int NWG = NW / STAGES, NPRE = (16 * 64 + NWG - 1) / NWG;
     const int g = tid / NWG, gt = tid - g * NWG;
-    // a thread's right-hand-side elements: slot q = gt + NWG i -> (jr, c) with c % 4 = q % 4 and jr % 8 = (q / 4) % 8 (the lanes of
-    // a warp spread over the banks of the core-matrix layout, 8 rows x 4 K-elements).  Offsets are per thread constants: element
-    // offset in a vector, operand offsets of the Re / Im rows (hi part; the lo part is the next row group) in Af and in Ad.
+    // a thread's right-hand-side elements: slot q = gt + NWG i -> (jr, c) with c % 4 = q % 4 and jr % 8 = (q / 4) % 8, i.e. the 32
+    // lanes of a warp store to 32 distinct banks of the core-matrix layout (8 rows x 4 K-elements).  Offsets are per thread
+    // constants: element offset in a vector, operand offsets of Re (row jr) / Im (row 12 + jr) in Bf and of the two rows in Bd.
     long voff[NPRE]; int o0[NPRE], o1[NPRE], d0[NPRE], d1[NPRE]; bool hi_half[NPRE];
 #pragma unroll
     for (int i = 0; i < NPRE; i++) {
       const int q = gt + NWG * i, rest = q >> 5;
       const int jr = (rest & 1) * 8 + ((q >> 2) & 7), c = (rest >> 1) * 4 + (q & 3);
       const bool ok = jr < NR && c < n;
-      const int kk = 2 * c, qg = jr / 3, jj = jr - 3 * qg;
-      const int rre = row_low(qg, jj, 0), rim = row_low(qg, jj, 1);
+      const int row1 = NR + jr, kk = 2 * c;
       voff[i] = ok ? (long)jr * vstride + c : -1;
-      o0[i] = ((2 * qg) * kcf + (c >> 2)) * 32 + rre * 4 + (c & 3);
-      o1[i] = ((2 * qg) * kcf + (c >> 2)) * 32 + rim * 4 + (c & 3);
-      d0[i] = ((2 * qg) * kcd + (kk >> 2)) * 32 + rre * 4 + (kk & 3);
-      d1[i] = ((2 * qg) * kcd + (kk >> 2)) * 32 + rim * 4 + (kk & 3);
+      o0[i] = ((jr >> 3) * kcf + (c >> 2)) * 32 + (jr & 7) * 4 + (c & 3);
+      o1[i] = ((row1 >> 3) * kcf + (c >> 2)) * 32 + (row1 & 7) * 4 + (c & 3);
+      d0[i] = ((jr >> 3) * kcd + (kk >> 2)) * 32 + (jr & 7) * 4 + (kk & 3);
+      d1[i] = ((row1 >> 3) * kcd + (kk >> 2)) * 32 + (row1 & 7) * 4 + (kk & 3);
       hi_half[i] = c >= nh;
     }
     // the right-hand sides a block multiplies (12 x n complex) are fetched one block of this group ahead into registers, the
@@ -387,16 +341,16 @@ k_coarse_mrhs(CoarseOp op, const float *__restrict__ T, cf *__restrict__ out, co
     };
     int src_next = 0;
     if (g < total) prefetch(source(g));
-    if (g + GROUPS < total) src_next = source(g + GROUPS);
-    for (int j = g; j < total; j += GROUPS) {
-      const int k = j / 5, m = j - 5 * k, s = j % STAGES, u = j / STAGES;
+    if (g + STAGES < total) src_next = source(g + STAGES);
+    for (int j = g; j < total; j += STAGES) {
+      const int k = j / 5, m = j - 5 * k, s = g, u = j / STAGES;
       float *stg = stage0 + (size_t)s * SF;
-      float *Bfh = stg + 8 * nn, *Bfl = Bfh + kcf * 32;                  // hi rows: row groups 2 q, lo rows: 2 q + 1
-      float *Bdh = Bd0 + (size_t)(k & 1) * BDF, *Bdl = Bdh + kcd * 32;
+      float *Bfh = stg + 8 * nn, *Bfl = Bfh + 32 * n;
+      float *Bdh = Bd0 + (size_t)(k & 1) * BDF, *Bdl = Bdh + 64 * n;
       if (u > 0) mbar_wait_bounded(&empty[s], (uint32_t)((u - 1) & 1));   // the MMAs that read this stage's B operands (and, in
                                                                          // order, everything before them) have completed
-      // forward operand rows Re V_j / Im V_j from the prefetched registers; for m = 0 these are the site's own vectors, from
-      // which the daggered operand rows [w | -i w], w = G5 V(x), are filled as well (K = rho = 2 r + re|im)
+      // forward B = [Re V | Im V] from the prefetched registers; for m = 0 these are the site's own vectors, from which
+      // the daggered operand B' = [w | -i w], w = G5 V(x), is filled as well (rows j and 12 + j, K = rho = 2 r + re|im)
 #pragma unroll
       for (int i = 0; i < NPRE; i++) {
         if (voff[i] >= 0) {
@@ -406,16 +360,16 @@ k_coarse_mrhs(CoarseOp op, const float *__restrict__ T, cf *__restrict__ out, co
           split_tf32(v.im, hi, lo); Bfh[o1[i]] = hi; Bfl[o1[i]] = lo;
           if (m == 0) {
             const cf w = hi_half[i] ? -v : v;
-            split_tf32(w.re, hi, lo);  Bdh[d0[i]] = hi;     Bdl[d0[i]] = lo;        // Re row: [ w.re,  w.im ]
+            split_tf32(w.re, hi, lo);  Bdh[d0[i]] = hi;     Bdl[d0[i]] = lo;        // row jr:      [ w.re,  w.im ]
             split_tf32(w.im, hi, lo);  Bdh[d0[i] + 1] = hi; Bdl[d0[i] + 1] = lo;
-            Bdh[d1[i]] = hi;           Bdl[d1[i]] = lo;                             // Im row: [ w.im, -w.re ]
+            Bdh[d1[i]] = hi;           Bdl[d1[i]] = lo;                             // row 12 + jr: [ w.im, -w.re ]
             split_tf32(-w.re, hi, lo); Bdh[d1[i] + 1] = hi; Bdl[d1[i] + 1] = lo;
           }
         }
       }
-      if (j + GROUPS < total) {
+      if (j + STAGES < total) {
         prefetch(src_next);
-        if (j + 2 * GROUPS < total) src_next = source(j + 2 * GROUPS);
+        if (j + 2 * STAGES < total) src_next = source(j + 2 * STAGES);
       }
       mbar_wait_bounded(&full[s], (uint32_t)(u & 1));
       // TF32 split of the image(s) into the operand set (RAW = 0: in place): hi = value truncated to 11 significant bits,
@@ -476,18 +430,17 @@ float *coarse_mrhs_tile(const CoarseOp &op) {
 bool coarse_apply_mrhs(const CoarseOp &op, const float *T, cf *out, const cf *in, cf *Z, long vstride, long zstride) {
   const int n = op.n;
   if (!coarse_mrhs_supported(op) || !T) return false;
-  // configurations (operand sets, landing buffers, worker groups): three operand sets filled in place (n <= 40), two operand
-  // sets + two landing buffers, two operand sets in place (n = 48), one (n >= 56)
+  // configurations: two operand sets + two landing buffers (n <= 40), two operand sets split in place (n = 48), one (n >= 56)
   const size_t limit = 226 * 1024;                                   // 227 KB per CTA minus the kernel's static shared memory
   int cfg = -1;
-  const int stages_of[4] = {3, 2, 2, 1}, raw_of[4] = {0, 2, 0, 0};
-  for (int c = 0; c < 4 && cfg < 0; c++)
+  const int stages_of[3] = {2, 2, 1}, raw_of[3] = {2, 0, 0};
+  for (int c = 0; c < 3 && cfg < 0; c++)
     if (mrhs::layout(n, stages_of[c], raw_of[c]).total <= limit) cfg = c;
-  static const char *force = getenv("DDA_MRHS_CONFIG");              // A/B runs: 0 .. 3
-  if (force && atoi(force) > cfg && atoi(force) < 4) cfg = atoi(force);
+  static const char *force = getenv("DDA_MRHS_CONFIG");              // A/B runs: 0, 1, 2
+  if (force && atoi(force) > cfg && atoi(force) < 3) cfg = atoi(force);
   if (cfg < 0) return false;
   const size_t smem = mrhs::layout(n, stages_of[cfg], raw_of[cfg]).total;
-  static size_t attr[4] = {0, 0, 0, 0};
+  static size_t attr[3] = {0, 0, 0};
   static int sms = 0;
   if (!sms) sms = dev_sm_count();
   const long grid = std::min<long>(op.V, (long)sms);                 // one CTA per SM: the CTA owns all 512 TMEM columns
@@ -495,10 +448,9 @@ bool coarse_apply_mrhs(const CoarseOp &op, const float *T, cf *out, const cf *in
     if (smem > attr[cfg]) { CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[cfg] = smem; }
     kern<<<(unsigned)grid, mrhs::NT, smem, g_stream>>>(op, T, out, in, Z, vstride, zstride, (int)op.V);
   };
-  if (cfg == 0) launch(mrhs::k_coarse_mrhs<3, 0, 2>);
-  else if (cfg == 1) launch(mrhs::k_coarse_mrhs<2, 2, 2>);
-  else if (cfg == 2) launch(mrhs::k_coarse_mrhs<2, 0, 2>);
-  else launch(mrhs::k_coarse_mrhs<1, 0, 1>);
+  if (cfg == 0) launch(mrhs::k_coarse_mrhs<2, 2>);
+  else if (cfg == 1) launch(mrhs::k_coarse_mrhs<2, 0>);
+  else launch(mrhs::k_coarse_mrhs<1, 0>);
   g_launch_count++;
   coarse_combine_batch(op, out, in, Z, mrhs::NR, vstride, zstride);
 #ifdef DDA_DEBUG_SYNC
